@@ -1,0 +1,149 @@
+"""ctypes loaders for the test oracle.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may import this
+module; the product package never does.
+
+  Oracle  — oracle/libphos_oracle.so, the plain-C restatement (phos_oracle.c).
+  RefLib  — oracle/_ref/libphos_ref.so, the reference's own sources compiled from /root/reference
+            (present when `make -C oracle ref` ran in a container that has the reference; the
+            built .so travels to the GPU box, the sources do not).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from phosphorus_mk2_b200.rays import PhosRays, RayBatch
+from phosphorus_mk2_b200.scene import PhosSceneDesc, Scene
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libphos_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libphos_ref.so")
+NODE_BYTES, PACKET_BYTES = 288, 384
+
+
+class Counters(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("nodes", C.c_uint64), ("packets", C.c_uint64),
+                ("triangles", C.c_uint64), ("max_stack", C.c_uint64)]
+
+
+def build(target: str = "oracle") -> None:
+    subprocess.run(["make", "-C", HERE, target], check=True, capture_output=True)
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build("oracle")
+        self.lib = L = C.CDLL(ORACLE_SO)
+        L.orc_brute_force.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(PhosRays), C.c_uint64]
+        L.orc_traverse.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PhosRays), C.c_uint64, C.POINTER(Counters), C.c_int]
+        L.orc_camera_rays.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(PhosRays)]
+        L.orc_sizeof_node.restype = C.c_uint32
+        L.orc_sizeof_packet.restype = C.c_uint32
+        assert L.orc_sizeof_node() == NODE_BYTES and L.orc_sizeof_packet() == PACKET_BYTES
+
+    def brute_force(self, packets: np.ndarray, rays: RayBatch) -> RayBatch:
+        out = rays.copy()
+        s = out.as_struct()
+        self.lib.orc_brute_force(packets.ctypes.data, len(packets) // PACKET_BYTES, C.byref(s), out.n)
+        return out
+
+    def traverse(self, nodes: np.ndarray, packets: np.ndarray, rays: RayBatch, ties: bool = True):
+        out = rays.copy()
+        s = out.as_struct()
+        c = Counters()
+        self.lib.orc_traverse(nodes.ctypes.data, packets.ctypes.data, C.byref(s), out.n, C.byref(c), 1 if ties else 0)
+        return out, c
+
+    def camera_rays(self, cam, x0=0, y0=0, w=None, h=None, jx=0.5, jy=0.5) -> RayBatch:
+        w = cam.film_width if w is None else w
+        h = cam.film_height if h is None else h
+        out = RayBatch(w * h)
+        s = out.as_struct()
+        m = (C.c_float * 16)(*np.asarray(cam.to_world, np.float32).ravel())
+        self.lib.orc_camera_rays(m, cam.fov, cam.film_width, cam.film_height, x0, y0, w, h, jx, jy, C.byref(s))
+        return out
+
+
+class RefScene:
+    """A scene inside the compiled reference: reference mesh_t/scene_t + its own mbvh_t."""
+
+    def __init__(self, lib, scene: Scene):
+        self.lib = lib
+        self._scene = scene
+        d = scene.desc()
+        self.h = lib.ref_scene_create(C.byref(d))
+        self.build_seconds = None
+
+    def build(self):
+        self.build_seconds = self.lib.ref_accel_build(self.h)
+        return self.build_seconds
+
+    def accel(self):
+        """(nodes288 bytes, packets384 bytes) exactly as the reference builder laid them out."""
+        nn, np_ = self.lib.ref_accel_num_nodes(self.h), self.lib.ref_accel_num_packets(self.h)
+        nodes = np.zeros(nn * NODE_BYTES, np.uint8)
+        packets = np.zeros(np_ * PACKET_BYTES, np.uint8)
+        self.lib.ref_accel_copy(self.h, nodes.ctypes.data, nn, packets.ctypes.data, np_)
+        return nodes, packets
+
+    def trace(self, rays: RayBatch, kind: str = "stream", threads: int = 1):
+        out = rays.copy()
+        f, u = out.float_ptrs()
+        secs = self.lib.ref_trace(self.h, 0 if kind == "stream" else 1, f, u, out.n, threads)
+        return out, secs
+
+    def render(self, spp: int, pps: int = 1, depth: int = 9, single_threaded: bool = True):
+        cam = self._scene.camera
+        img = np.zeros((cam.film_height, cam.film_width, 4), np.float32)
+        secs = self.lib.ref_render(self.h, spp, pps, depth, 1 if single_threaded else 0, img.ctypes.data)
+        return img, secs
+
+    def num_lights(self):
+        return self.lib.ref_scene_num_lights(self.h)
+
+    def __del__(self):
+        try:
+            self.lib.ref_scene_destroy(self.h)
+        except Exception:
+            pass
+
+
+class RefLib:
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        self.lib = L = C.CDLL(REF_SO)
+        L.ref_scene_create.restype = C.c_void_p
+        L.ref_scene_create.argtypes = [C.POINTER(PhosSceneDesc)]
+        L.ref_scene_destroy.argtypes = [C.c_void_p]
+        L.ref_scene_num_lights.argtypes = [C.c_void_p]
+        L.ref_scene_num_lights.restype = C.c_uint32
+        L.ref_accel_build.argtypes = [C.c_void_p]
+        L.ref_accel_build.restype = C.c_double
+        for fn in (L.ref_accel_num_nodes, L.ref_accel_num_packets):
+            fn.argtypes = [C.c_void_p]
+            fn.restype = C.c_uint32
+        L.ref_accel_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.ref_trace.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_uint32)),
+                                C.c_uint64, C.c_int]
+        L.ref_trace.restype = C.c_double
+        L.ref_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+        L.ref_render.restype = C.c_double
+        L.ref_hardware_concurrency.restype = C.c_uint32
+        L.ref_sizeof_node.restype = C.c_uint32
+        L.ref_sizeof_packet.restype = C.c_uint32
+        assert L.ref_sizeof_node() == NODE_BYTES and L.ref_sizeof_packet() == PACKET_BYTES
+
+    def scene(self, scene: Scene) -> RefScene:
+        return RefScene(self.lib, scene)
+
+    def hardware_concurrency(self) -> int:
+        return int(self.lib.ref_hardware_concurrency())

@@ -1,0 +1,279 @@
+// TEST INFRASTRUCTURE ONLY (oracle/_ref build).  Never linked into the product.
+//
+// A thin extern "C" face over the UNMODIFIED reference sources compiled where they lie under
+// /root/reference/src (see oracle/Makefile).  Everything that computes here is the reference's
+// own code: mesh_t::builder_t (src/mesh.hpp:46-66), scene_t (src/scene.hpp), bvh::from
+// (src/accel/bvh/binned_sah_builder.hpp:272-281), stream_mbvh_kernel_t / linear_mbvh_kernel_t
+// (src/kernels/cpu/*_bvh_kernel.cpp), cpu_t (src/xpu/cpu.cpp).  This file only moves flat arrays
+// in and out so Python tests and bench.py's reference arm can drive it through ctypes.
+#include "../../include/phos_scene.h"
+
+#include "accel/bvh.hpp"
+#include "accel/bvh/binned_sah_builder.hpp"
+#include "accel/triangle.hpp"
+#include "kernels/cpu/linear_bvh_kernel.hpp"
+#include "kernels/cpu/stream_bvh_kernel.hpp"
+#include "light.hpp"
+#include "material.hpp"
+#include "mesh.hpp"
+#include "options.hpp"
+#include "scene.hpp"
+#include "state.hpp"
+#include "xpu/cpu.hpp"
+
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct ref_scene {
+  scene_t scene;
+  accel::mbvh_t accel;
+  bool built = false;
+  double build_seconds = 0.0;
+};
+
+void fill_scene(scene_t& scene, const phos_scene_desc* d) {
+  for (uint32_t i = 0; i < d->num_materials; ++i) {
+    const phos_material& m = d->materials[i];
+    auto* mat = new material_t();
+    material_t::builder_t::scoped_t b(mat->builder());
+    const char* node = m.kind == PHOS_MAT_EMITTER ? "diffuse_emitter_node"
+                     : m.kind == PHOS_MAT_GLOSSY ? "glossy_bsdf_node" : "diffuse_bsdf_node";
+    b->shader(node, "layer0", "surface");
+    b->parameter("Cs", Imath::Color3f(m.cs[0], m.cs[1], m.cs[2]));
+    b->parameter("roughness", m.roughness);
+    b->parameter("power", m.power);
+    scene.add("material" + std::to_string(i), mat);
+  }
+  for (uint32_t m = 0; m < d->num_meshes; ++m) {
+    auto* mesh = new mesh_t();
+    {
+      mesh_t::builder_t::scoped_t b(mesh->builder());
+      for (uint32_t v = d->vert_offset[m]; v < d->vert_offset[m + 1]; ++v) {
+        b->add_vertex(Imath::V3f(d->vertices[3 * v], d->vertices[3 * v + 1], d->vertices[3 * v + 2]));
+        if (d->normals) {
+          b->add_normal(Imath::V3f(d->normals[3 * v], d->normals[3 * v + 1], d->normals[3 * v + 2]));
+        }
+      }
+      const bool smooth = d->mesh_smooth[m] != 0;
+      for (uint32_t f = d->face_offset[m]; f < d->face_offset[m + 1]; ++f) {
+        b->add_face(d->faces[3 * f], d->faces[3 * f + 1], d->faces[3 * f + 2], smooth);
+      }
+      for (uint32_t s = d->set_offset[m]; s < d->set_offset[m + 1]; ++s) {
+        std::vector<uint32_t> faces(d->set_faces + d->set_face_offset[s], d->set_faces + d->set_face_offset[s + 1]);
+        b->add_face_set(d->set_material[s], faces);
+      }
+      b->set_normals_per_vertex();
+    }
+    scene.add(mesh);
+  }
+  camera_t& c = scene.camera;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) c.to_world.x[i][j] = d->camera.to_world[4 * i + j];
+  c.fov = d->camera.fov;
+  c.focal_distance = d->camera.focal_distance;
+  c.aperture_radius = d->camera.aperture_radius;
+  c.film.width = d->camera.film_width;
+  c.film.height = d->camera.film_height;
+  scene.preprocess();
+}
+
+// view of one 1024-slot window of flat SoA arrays as the reference's ray_t<1024>
+void load_stream(ray_t<>* r, const phos_scene_desc*, const float* const* f, const uint32_t* const* u, size_t base,
+                 uint32_t n) {
+  memcpy(r->p.x, f[0] + base, n * 4);
+  memcpy(r->p.y, f[1] + base, n * 4);
+  memcpy(r->p.z, f[2] + base, n * 4);
+  memcpy(r->wi.x, f[3] + base, n * 4);
+  memcpy(r->wi.y, f[4] + base, n * 4);
+  memcpy(r->wi.z, f[5] + base, n * 4);
+  memcpy(r->d, f[6] + base, n * 4);
+  memcpy(r->u, f[7] + base, n * 4);
+  memcpy(r->v, f[8] + base, n * 4);
+  memcpy(r->mesh, u[0] + base, n * 4);
+  memcpy(r->face, u[1] + base, n * 4);
+  memcpy(r->flags, u[2] + base, n * 4);
+}
+
+void store_stream(const ray_t<>* r, float* const* f, uint32_t* const* u, size_t base, uint32_t n) {
+  memcpy(f[6] + base, r->d, n * 4);
+  memcpy(f[7] + base, r->u, n * 4);
+  memcpy(f[8] + base, r->v, n * 4);
+  memcpy(u[0] + base, r->mesh, n * 4);
+  memcpy(u[1] + base, r->face, n * 4);
+  memcpy(u[2] + base, r->flags, n * 4);
+}
+
+struct memory_film_t : public film_t<> {
+  float* rgba;  // W*H*4, row-major
+  uint32_t width, height;
+  void add_tile(const Imath::V2i& pos, const Imath::V2i& size, const render_buffer_t& buffer) override {
+    const auto* ch = buffer.channel(render_buffer_t::PRIMARY);
+    for (int y = 0; y < size.y; ++y)
+      for (int x = 0; x < size.x; ++x) {
+        float px[4] = {0, 0, 0, 0};
+        ch->get(x, y, px);
+        float* out = rgba + 4 * ((size_t)(pos.y + y) * width + (pos.x + x));
+        out[0] = px[0]; out[1] = px[1]; out[2] = px[2]; out[3] = 1.0f;
+      }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void* ref_scene_create(const phos_scene_desc* desc) {
+  auto* s = new ref_scene();
+  fill_scene(s->scene, desc);
+  return s;
+}
+
+void ref_scene_destroy(void* h) { delete static_cast<ref_scene*>(h); }
+
+uint32_t ref_scene_num_lights(void* h) { return static_cast<ref_scene*>(h)->scene.num_lights(); }
+
+// cpu_t::details_t::reset (src/xpu/cpu.cpp:35-44)
+double ref_accel_build(void* h) {
+  auto* s = static_cast<ref_scene*>(h);
+  const auto t0 = std::chrono::steady_clock::now();
+  s->accel.reset();
+  {
+    accel::mbvh_t::builder_t::scoped_t builder(s->accel.builder());
+    std::vector<triangle_t> triangles;
+    s->scene.triangles(triangles);
+    bvh::from(builder, triangles);
+  }
+  s->built = true;
+  s->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return s->build_seconds;
+}
+
+uint32_t ref_accel_num_packets(void* h) { return static_cast<ref_scene*>(h)->accel.num_triangles; }
+
+// num_nodes is never published by the reference (src/accel/bvh.cpp:42-47); recover it by walking.
+uint32_t ref_accel_num_nodes(void* h) {
+  auto* s = static_cast<ref_scene*>(h);
+  if (!s->accel.root) return 0;
+  uint32_t max_index = 0;
+  std::vector<uint32_t> stack{0};
+  while (!stack.empty()) {
+    const uint32_t n = stack.back();
+    stack.pop_back();
+    if (n > max_index) max_index = n;
+    const auto& node = s->accel.root[n];
+    for (int i = 0; i < 8; ++i) {
+      const bool empty = node.bounds[i] > node.bounds[i + 24];
+      if (!empty && node.flags[i] != 1) stack.push_back(node.offset[i]);
+    }
+  }
+  return max_index + 1;
+}
+
+uint32_t ref_sizeof_node(void) { return sizeof(mbvh::node_t<8>); }
+uint32_t ref_sizeof_packet(void) { return sizeof(accel::mbvh_t::triangle_t); }
+
+void ref_accel_copy(void* h, void* nodes, uint32_t n_nodes, void* packets, uint32_t n_packets) {
+  auto* s = static_cast<ref_scene*>(h);
+  memcpy(nodes, s->accel.root, (size_t)n_nodes * sizeof(mbvh::node_t<8>));
+  memcpy(packets, s->accel.triangles, (size_t)n_packets * sizeof(accel::mbvh_t::triangle_t));
+}
+
+// Trace n rays given as flat SoA arrays, cut into 1024-ray streams (config::STREAM_SIZE), on
+// `threads` host threads each owning one kernel instance and pulling streams from an atomic cursor
+// — the shape of cpu_t::start (src/xpu/cpu.cpp:223-238).  kind 0 = stream_mbvh_kernel_t,
+// 1 = linear_mbvh_kernel_t (brute force).  f[0..8] = px,py,pz,wx,wy,wz,d,u,v ; u[0..2] = mesh,face,flags.
+// Returns seconds spent tracing (excludes thread start-up of kernel state allocation).
+double ref_trace(void* h, int kind, float* const* f, uint32_t* const* u, uint64_t n, int threads) {
+  auto* s = static_cast<ref_scene*>(h);
+  const uint64_t streams = (n + 1023) / 1024;
+  std::atomic<uint64_t> cursor(0);
+  if (threads < 1) threads = 1;
+  std::atomic<int> ready(0);
+  std::atomic<bool> go(false);
+  std::vector<std::thread> pool;
+  std::chrono::steady_clock::time_point t0;
+  for (int t = 0; t < threads; ++t) {
+    pool.emplace_back([&, kind]() {
+      stream_mbvh_kernel_t stream_kernel(&s->accel);
+      linear_mbvh_kernel_t linear_kernel(&s->accel);
+      ray_t<>* rays;
+      posix_memalign((void**)&rays, 32, sizeof(ray_t<>));
+      active_t<> active;
+      ++ready;
+      while (!go.load()) std::this_thread::yield();
+      for (;;) {
+        const uint64_t i = cursor++;
+        if (i >= streams) break;
+        const size_t base = (size_t)i * 1024;
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(1024, n - base);
+        load_stream(rays, nullptr, f, u, base, cnt);
+        active.reset(0);
+        active.num = cnt;
+        if (kind == 0) {
+          stream_kernel.trace(rays, active);
+        } else {
+          // the linear kernel has no MASKED filter of its own (src/kernels/cpu/linear_bvh_kernel.cpp:14-19):
+          // hand it only the unmasked slots, as lanes_t::init does for the stream kernel.
+          active_t<> unmasked;
+          for (uint32_t k = 0; k < cnt; ++k)
+            if (!rays->is_masked(k)) unmasked.add(k);
+          linear_kernel.trace(rays, unmasked);
+        }
+        store_stream(rays, f, u, base, cnt);
+      }
+      free(rays);
+    });
+  }
+  while (ready.load() < threads) std::this_thread::yield();
+  t0 = std::chrono::steady_clock::now();
+  go.store(true);
+  for (auto& th : pool) th.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// Render a frame with the reference's own CPU device (cpu_t::preprocess/start/join) into an RGBA
+// float image.  Wall clock around start -> join like src/core.cpp:158-177.  Returns seconds.
+double ref_render(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, float* rgba) {
+  auto* s = static_cast<ref_scene*>(h);
+  parsed_options_t options;
+  options.samples_per_pixel = spp;
+  options.paths_per_sample = pps;
+  options.path_depth = depth;
+  options.single_threaded = single_threaded != 0;
+  options.host_only = true;
+
+  const uint32_t W = s->scene.camera.film.width, H = s->scene.camera.film.height;
+  render_buffer_t::descriptor_t format;
+  format.request(render_buffer_t::PRIMARY, 4);
+
+  cpu_t* device = cpu_t::make(options);
+  device->preprocess(s->scene);
+
+  job::tiles_t* tiles = job::tiles_t::make(W, H, 32, format);
+  memory_film_t film;
+  film.rgba = rgba;
+  film.width = W;
+  film.height = H;
+  sampler_t* sampler = new sampler_t(options);
+  frame_state_t state(sampler, tiles, &film);
+  sampler->preprocess(s->scene);
+
+  const auto t0 = std::chrono::steady_clock::now();
+  device->start(s->scene, state);
+  device->join();
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  delete device;
+  delete tiles;
+  // sampler_t::~sampler_t deletes posix_memalign'd memory (src/sampling.cpp:83-87); leak it instead.
+  return dt;
+}
+
+uint32_t ref_hardware_concurrency(void) { return std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+"""Host-side scene model: the reference's scene/mesh/material/camera API, flattened for the C ABI.
+
+Mirrors the names and meaning of the reference's public scene API so tests read like the
+reference's own callers (reference: src/scene.hpp:14-50 ``scene_t``, src/mesh.hpp:15-138
+``mesh_t`` + ``builder_t``, src/material.hpp ``material_t``, src/entities/camera.hpp:10-40
+``camera_t``).  Geometry is held in numpy arrays (10-30 M triangle scenes) and handed to the native
+library as one ``phos_scene_desc`` (include/phos_scene.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+MAT_DIFFUSE, MAT_GLOSSY, MAT_EMITTER = 0, 1, 2
+
+
+class PhosMaterial(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("cs", C.c_float * 3), ("roughness", C.c_float), ("power", C.c_float)]
+
+
+class PhosCamera(C.Structure):
+    _fields_ = [
+        ("to_world", C.c_float * 16),
+        ("fov", C.c_float),
+        ("focal_distance", C.c_float),
+        ("aperture_radius", C.c_float),
+        ("film_width", C.c_uint32),
+        ("film_height", C.c_uint32),
+    ]
+
+
+class PhosSceneDesc(C.Structure):
+    _fields_ = [
+        ("num_meshes", C.c_uint32),
+        ("vert_offset", C.POINTER(C.c_uint32)),
+        ("vertices", C.POINTER(C.c_float)),
+        ("normals", C.POINTER(C.c_float)),
+        ("face_offset", C.POINTER(C.c_uint32)),
+        ("faces", C.POINTER(C.c_uint32)),
+        ("mesh_smooth", C.POINTER(C.c_uint8)),
+        ("set_offset", C.POINTER(C.c_uint32)),
+        ("set_material", C.POINTER(C.c_uint32)),
+        ("set_face_offset", C.POINTER(C.c_uint32)),
+        ("set_faces", C.POINTER(C.c_uint32)),
+        ("num_materials", C.c_uint32),
+        ("materials", C.POINTER(PhosMaterial)),
+        ("camera", PhosCamera),
+    ]
+
+
+@dataclass
+class Material:
+    """One of the renderer's built-in closures (include/phos_scene.h PHOS_MAT_*)."""
+
+    kind: int
+    cs: tuple = (1.0, 1.0, 1.0)
+    roughness: float = 0.0
+    power: float = 1.0
+
+    def is_emitter(self) -> bool:  # material_t::is_emitter, src/material.cpp:487-489
+        return self.kind == MAT_EMITTER
+
+
+@dataclass
+class Mesh:
+    """mesh_t: vertices, faces and face sets (material id -> faces), src/mesh.hpp:68-77."""
+
+    vertices: np.ndarray  # (nv, 3) float32
+    faces: np.ndarray  # (nf, 3) uint32, mesh-local
+    sets: list  # [(material_id, face_index_array)] in set order
+    smooth: bool = False
+    normals: np.ndarray | None = None  # (nv, 3) float32, per vertex
+
+    def __post_init__(self):
+        self.vertices = np.ascontiguousarray(self.vertices, dtype=np.float32).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(self.faces, dtype=np.uint32).reshape(-1, 3)
+        self.sets = [(int(m), np.ascontiguousarray(f, dtype=np.uint32).ravel()) for m, f in self.sets]
+        if self.normals is not None:
+            self.normals = np.ascontiguousarray(self.normals, dtype=np.float32).reshape(-1, 3)
+            assert len(self.normals) == len(self.vertices)
+        if self.smooth:
+            assert self.normals is not None, "smooth faces interpolate per-vertex normals"
+
+    @property
+    def num_faces(self) -> int:
+        return len(self.faces)
+
+
+@dataclass
+class Camera:
+    """camera_t. ``to_world`` uses Imath's row-vector convention (translation in row 3)."""
+
+    to_world: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    fov: float = math.radians(39.3)
+    film_width: int = 512
+    film_height: int = 512
+    focal_distance: float = 1.0
+    aperture_radius: float = 0.0
+
+    @staticmethod
+    def look_at(eye, target, up=(0.0, 1.0, 0.0)) -> np.ndarray:
+        """Row-vector camera-to-world matrix for a camera looking down its local -z."""
+        eye = np.asarray(eye, dtype=np.float64)
+        f = np.asarray(target, dtype=np.float64) - eye
+        f /= np.linalg.norm(f)
+        r = np.cross(f, np.asarray(up, dtype=np.float64))
+        r /= np.linalg.norm(r)
+        u = np.cross(r, f)
+        m = np.eye(4)
+        m[0, :3], m[1, :3], m[2, :3], m[3, :3] = r, u, -f, eye
+        return m.astype(np.float32)
+
+
+class Scene:
+    """scene_t: flat list of meshes, materials and one camera (src/scene.hpp:14-50)."""
+
+    def __init__(self):
+        self.meshes: list[Mesh] = []
+        self.materials: list[Material] = []
+        self.camera = Camera()
+        self._keep = None
+
+    # scene_t::add(name, material) / add(mesh): ids are assigned in insertion order (scene.cpp:85-98)
+    def add_material(self, material: Material) -> int:
+        self.materials.append(material)
+        return len(self.materials) - 1
+
+    def add(self, mesh: Mesh) -> int:
+        assert len(self.meshes) < 0xFFFF, "meshid is packed into 16 bits (src/accel/triangle.hpp:62-66)"
+        self.meshes.append(mesh)
+        return len(self.meshes) - 1
+
+    def num_meshes(self) -> int:
+        return len(self.meshes)
+
+    def num_materials(self) -> int:
+        return len(self.materials)
+
+    def num_triangles(self) -> int:
+        return sum(sum(len(f) for _, f in m.sets) for m in self.meshes)
+
+    def desc(self) -> PhosSceneDesc:
+        """Flatten into a phos_scene_desc; the backing arrays stay alive on ``self``."""
+        nm = len(self.meshes)
+        vert_offset = np.zeros(nm + 1, np.uint32)
+        face_offset = np.zeros(nm + 1, np.uint32)
+        set_offset = np.zeros(nm + 1, np.uint32)
+        for i, m in enumerate(self.meshes):
+            vert_offset[i + 1] = vert_offset[i] + len(m.vertices)
+            face_offset[i + 1] = face_offset[i] + len(m.faces)
+            set_offset[i + 1] = set_offset[i] + len(m.sets)
+        vertices = np.concatenate([m.vertices for m in self.meshes]).astype(np.float32, copy=False)
+        has_normals = all(m.normals is not None for m in self.meshes)
+        normals = np.concatenate([m.normals for m in self.meshes]) if has_normals else None
+        if not has_normals:
+            assert not any(m.smooth for m in self.meshes), "smooth meshes need normals on every mesh"
+        faces = np.concatenate([m.faces for m in self.meshes]).astype(np.uint32, copy=False)
+        smooth = np.array([1 if m.smooth else 0 for m in self.meshes], np.uint8)
+        set_material, set_faces_l = [], []
+        for m in self.meshes:
+            for mat, f in m.sets:
+                assert 0 <= mat < len(self.materials)
+                set_material.append(mat)
+                set_faces_l.append(f)
+        set_material = np.array(set_material, np.uint32)
+        set_face_offset = np.zeros(len(set_faces_l) + 1, np.uint32)
+        set_face_offset[1:] = np.cumsum([len(f) for f in set_faces_l])
+        set_faces = np.concatenate(set_faces_l).astype(np.uint32, copy=False) if set_faces_l else np.zeros(0, np.uint32)
+        mats = (PhosMaterial * max(1, len(self.materials)))()
+        for i, m in enumerate(self.materials):
+            mats[i].kind = m.kind
+            mats[i].cs = (C.c_float * 3)(*m.cs)
+            mats[i].roughness = m.roughness
+            mats[i].power = m.power
+
+        def p(a, t):
+            return a.ctypes.data_as(C.POINTER(t)) if a is not None else C.POINTER(t)()
+
+        vertices = np.ascontiguousarray(vertices)
+        faces = np.ascontiguousarray(faces)
+        d = PhosSceneDesc()
+        d.num_meshes = nm
+        d.vert_offset = p(vert_offset, C.c_uint32)
+        d.vertices = p(vertices, C.c_float)
+        normals = np.ascontiguousarray(normals, dtype=np.float32) if normals is not None else None
+        d.normals = p(normals, C.c_float)
+        d.face_offset = p(face_offset, C.c_uint32)
+        d.faces = p(faces, C.c_uint32)
+        d.mesh_smooth = p(smooth, C.c_uint8)
+        d.set_offset = p(set_offset, C.c_uint32)
+        d.set_material = p(set_material, C.c_uint32)
+        d.set_face_offset = p(set_face_offset, C.c_uint32)
+        d.set_faces = p(set_faces, C.c_uint32)
+        d.num_materials = len(self.materials)
+        d.materials = C.cast(mats, C.POINTER(PhosMaterial))
+        cam = self.camera
+        d.camera.to_world = (C.c_float * 16)(*np.asarray(cam.to_world, np.float32).ravel())
+        d.camera.fov = cam.fov
+        d.camera.focal_distance = cam.focal_distance
+        d.camera.aperture_radius = cam.aperture_radius
+        d.camera.film_width = cam.film_width
+        d.camera.film_height = cam.film_height
+        self._keep = (vert_offset, vertices, normals, face_offset, faces, smooth, set_offset, set_material,
+                      set_face_offset, set_faces, mats)
+        return d
