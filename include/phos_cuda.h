@@ -1,0 +1,141 @@
+/* phos_cuda.h — C ABI of libphos_cuda.so, the B200 (sm_100a) device backend for phosphorus.
+ *
+ * This is what the reference's GPU device slot binds.  The reference declares `cuda_t : xpu_t`
+ * (src/xpu/cuda.hpp:8-13) with empty bodies (src/xpu/cuda.cpp:5-14); the drop-in fills
+ * `cuda_t::{make,preprocess,start,join}` by calling the entry points below (INTEGRATION.md shows
+ * the exact glue).  Plain C types only, int status everywhere (0 = PHOS_OK), no exceptions cross
+ * the boundary, caller-owned host buffers, one context per GPU, one host thread per context.
+ *
+ * Reference interface each group replaces / serves:
+ *   phos_cuda_device_count/create/destroy .. cuda_t::make + xpu_t::discover (src/xpu.cpp:7-9,
+ *                                            src/xpu/cuda.cpp:10-14), options from parsed_options_t
+ *                                            (src/options.hpp:6-43)
+ *   phos_bvh_*  ............................ cpu_t::details_t::reset (src/xpu/cpu.cpp:35-44): the
+ *                                            host binned-SAH 8-wide build, bvh::from
+ *                                            (src/accel/bvh/binned_sah_builder.hpp:215-281) +
+ *                                            accel::builder_t (src/accel/bvh.cpp:22-79); emits the
+ *                                            reference's own node_t<8> (288 B) / packet (384 B) arrays
+ *   phos_cuda_upload_accel ................. xpu_t::preprocess (src/xpu.hpp:20): takes mbvh_t::root /
+ *                                            mbvh_t::triangles (src/accel/bvh.hpp:29-36) as they are
+ *   phos_cuda_trace[_device] ............... stream_mbvh_kernel_t::trace(ray_t<>*, active_t<>&)
+ *                                            (src/kernels/cpu/stream_bvh_kernel.hpp:19-25): same SoA
+ *                                            fields, same flag semantics, in place
+ *   phos_cuda_upload_scene ................. what tile_renderer_t reads from scene_t while rendering
+ *                                            (src/xpu/cpu.cpp:85-99, deferred_shading_kernel.hpp, spt.hpp)
+ *   phos_cuda_camera_rays .................. camera::perspective_kernel_t (src/kernels/cpu/camera.hpp:78-159)
+ *   phos_cuda_render ....................... tile_renderer_t::render_tile over a list of tiles
+ *                                            (src/xpu/cpu.cpp:156-205), i.e. xpu_t::start's work
+ *   phos_cuda_film_* ....................... film_t<>::add_tile hand-off (src/film.hpp:10-16)
+ */
+#ifndef PHOS_CUDA_H
+#define PHOS_CUDA_H
+
+#include <stdint.h>
+
+#include "phos_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHOS_OK 0
+#define PHOS_ERR_INVALID 1  /* bad argument / call order                        */
+#define PHOS_ERR_CUDA 2     /* a CUDA runtime call failed (see last_error)      */
+#define PHOS_ERR_NO_DEVICE 3 /* no CUDA device: there is NO CPU fallback         */
+#define PHOS_ERR_ACCEL 4    /* malformed acceleration structure                 */
+
+/* ray flag bits, src/state.hpp:33-36 */
+#define PHOS_HIT 1u
+#define PHOS_MASKED 2u
+#define PHOS_SHADOW 4u
+#define PHOS_SPECULAR 8u
+
+typedef struct phos_ctx phos_ctx;
+typedef struct phos_bvh phos_bvh;
+
+/* the parsed_options_t fields a device reads (src/options.hpp:27-32) */
+typedef struct phos_options {
+  uint32_t samples_per_pixel; /* default 16 */
+  uint32_t paths_per_sample;  /* default 16; film is divided by spp*pps (src/xpu/cpu.cpp:191) */
+  uint32_t path_depth;        /* default 9  */
+} phos_options;
+
+/* A ray stream: the fields of ray_t<N> (src/state.hpp:39-57) as 12 SoA pointers over n rays.
+ * d = tmax in / hit distance out (FLT_MAX default); mesh = meshid | matid << 16; face = 3 * face index. */
+typedef struct phos_rays {
+  float *px, *py, *pz;
+  float *wx, *wy, *wz;
+  float* d;
+  uint32_t *mesh, *face;
+  float *u, *v;
+  uint32_t* flags;
+} phos_rays;
+
+/* job::tiles_t::tile_t (src/jobs/tiles.hpp:13-20) */
+typedef struct phos_tile {
+  uint32_t x, y, w, h;
+} phos_tile;
+
+typedef struct phos_accel_stats {
+  uint32_t ref_nodes, ref_packets;  /* as uploaded (288 B / 384 B records)                  */
+  uint32_t nodes, triangles;        /* as packed for the GPU (80 B / 48 B records)          */
+  uint32_t max_depth;               /* node levels below the root, sizes the traversal stack */
+  uint32_t max_leaf_triangles;
+  uint64_t bytes_nodes, bytes_triangles;
+  double   repack_seconds, upload_seconds;
+} phos_accel_stats;
+
+/* ---- device discovery / lifetime ------------------------------------------------------------ */
+int         phos_cuda_device_count(void);
+phos_ctx*   phos_cuda_create(int device, const phos_options* options); /* NULL on failure */
+void        phos_cuda_destroy(phos_ctx* ctx);
+const char* phos_cuda_last_error(phos_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+
+/* ---- host BVH build (the CPU build the reference keeps) --------------------------------------- */
+phos_bvh*   phos_bvh_build(const phos_scene_desc* scene, int threads /* <=0: hardware concurrency */);
+uint32_t    phos_bvh_num_nodes(const phos_bvh* bvh);
+uint32_t    phos_bvh_num_packets(const phos_bvh* bvh);
+const void* phos_bvh_nodes(const phos_bvh* bvh);   /* num_nodes   x 288 B, mbvh::node_t<8> layout        */
+const void* phos_bvh_packets(const phos_bvh* bvh); /* num_packets x 384 B, moeller_trumbore_t<8> layout  */
+double      phos_bvh_build_seconds(const phos_bvh* bvh);
+void        phos_bvh_free(phos_bvh* bvh);
+
+/* ---- acceleration structure upload (re-pack on host, one upload) ----------------------------- */
+int phos_cuda_upload_accel(phos_ctx* ctx, const void* nodes288, uint32_t n_nodes, const void* packets384,
+                           uint32_t n_packets);
+int phos_cuda_accel_stats(phos_ctx* ctx, phos_accel_stats* out);
+
+/* ---- ray queries ----------------------------------------------------------------------------- */
+/* Trace n rays in place.  Per ray, exactly as the reference's trace(rays, active):
+ *   MASKED            -> not traced, untouched;
+ *   SHADOW            -> any-hit: on an accepted hit set HIT and shrink d, leave mesh/face/u/v alone;
+ *   otherwise         -> closest hit: set HIT, d, mesh, face, u, v.
+ * `rays` holds HOST pointers; the call copies all twelve arrays in (48 B/ray: the surface record of
+ * a ray that is not hit must come back as it was), traces, copies out d, flags, mesh, face, u, v
+ * (24 B/ray), chunked so copies overlap traversal.  Blocking. */
+int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n);
+/* Same, `rays` holds DEVICE pointers of this ctx's device; asynchronous on the ctx stream. */
+int phos_cuda_trace_device(phos_ctx* ctx, const phos_rays* rays, uint64_t n);
+
+/* ---- device buffers for callers that keep ray streams resident ------------------------------- */
+int phos_cuda_rays_alloc(phos_ctx* ctx, uint64_t n, phos_rays* out_device_rays);
+int phos_cuda_rays_free(phos_ctx* ctx, phos_rays* device_rays);
+int phos_cuda_rays_upload(phos_ctx* ctx, const phos_rays* host, const phos_rays* device, uint64_t n);   /* inputs  */
+int phos_cuda_rays_download(phos_ctx* ctx, const phos_rays* device, const phos_rays* host, uint64_t n); /* outputs */
+int phos_cuda_synchronize(phos_ctx* ctx);
+/* CUDA-event timing on the ctx stream (bench.py's device clock): begin, work, end -> milliseconds */
+int phos_cuda_timer_begin(phos_ctx* ctx);
+int phos_cuda_timer_end(phos_ctx* ctx, float* out_ms);
+/* number of kernels this library launched on ctx since creation */
+uint64_t phos_cuda_launch_count(phos_ctx* ctx);
+/* Trace device-resident rays with traversal counters on: total 8-wide nodes box-tested and
+ * triangles Moeller-Trumbore-tested over the batch (the N_node / N_tri of the roofline model).  Blocking. */
+int phos_cuda_trace_count(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint64_t* out_nodes, uint64_t* out_tris);
+/* page-locked host memory for ray streams handed to phos_cuda_trace (pageable memory works, slower) */
+void* phos_cuda_host_alloc(uint64_t bytes);
+void  phos_cuda_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHOS_CUDA_H */

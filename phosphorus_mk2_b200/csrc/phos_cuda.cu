@@ -1,0 +1,342 @@
+// phos_cuda.cu — the C ABI of libphos_cuda.so (include/phos_cuda.h): context, acceleration-structure
+// upload, ray-stream buffers and the trace entry points.  No CPU fallback exists anywhere in this
+// library: without a CUDA device every entry point fails with PHOS_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/phos_cuda.h"
+#include "ctx.hpp"
+#include "phos_internal.hpp"
+#include "trace.cuh"
+
+namespace phos {
+
+std::string g_create_error;
+
+bool cuda_ok(phos_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  if (ctx) ctx->err = buf;
+  else g_create_error = buf;
+  return false;
+}
+
+int fail(phos_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+void free_rays(phos_rays& r) {
+  if (r.px) cudaFree(r.px);  // one slab, see alloc_rays
+  memset(&r, 0, sizeof(r));
+}
+
+// 12 arrays of n 32-bit values in one allocation, each starting on a 256-byte boundary
+bool alloc_rays(phos_ctx* ctx, uint64_t n, phos_rays& out) {
+  const uint64_t stride = (n * 4 + 255) / 256 * 256;
+  char* base = nullptr;
+  if (!cuda_ok(ctx, cudaMalloc(&base, std::max<uint64_t>(stride, 256) * 12), "cudaMalloc(ray stream)")) return false;
+  float** f[] = {&out.px, &out.py, &out.pz, &out.wx, &out.wy, &out.wz, &out.d};
+  for (int i = 0; i < 7; ++i) *f[i] = (float*)(base + stride * i);
+  out.mesh = (uint32_t*)(base + stride * 7);
+  out.face = (uint32_t*)(base + stride * 8);
+  out.u = (float*)(base + stride * 9);
+  out.v = (float*)(base + stride * 10);
+  out.flags = (uint32_t*)(base + stride * 11);
+  return true;
+}
+
+static const void* in_ptr(const phos_rays& r, int k) {
+  const void* p[] = {r.px, r.py, r.pz, r.wx, r.wy, r.wz, r.d, r.flags, r.mesh, r.face, r.u, r.v};
+  return p[k];
+}
+static void* out_ptr(const phos_rays& r, int k) {
+  void* p[] = {r.d, r.flags, r.mesh, r.face, r.u, r.v};
+  return p[k];
+}
+
+int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t stream, unsigned long long* cursor,
+                 bool count) {
+  if (n == 0) return PHOS_OK;
+  TraceArgs a;
+  a.rays = dev;
+  a.n = n;
+  a.accel.nodes = (const uint4*)ctx->d_nodes;
+  a.accel.tris = (const uint4*)ctx->d_tris;
+  a.cursor = cursor;
+  a.counters = ctx->d_counters;
+  if (!cuda_ok(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream), "memset(cursor)")) return PHOS_ERR_CUDA;
+  const uint64_t want = (n + kTraceBlock - 1) / kTraceBlock;
+  const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * ctx->trace_blocks_per_sm);
+  if (count) trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(a);
+  else trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(a);
+  ctx->launches++;
+  if (!cuda_ok(ctx, cudaGetLastError(), "trace_kernel launch")) return PHOS_ERR_CUDA;
+  return PHOS_OK;
+}
+
+}  // namespace phos
+
+using namespace phos;
+
+extern "C" {
+
+int phos_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* phos_cuda_last_error(phos_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+phos_ctx* phos_cuda_create(int device, const phos_options* options) {
+  const int n = phos_cuda_device_count();
+  if (n <= 0) {
+    g_create_error = "no CUDA device visible: libphos_cuda has no CPU fallback";
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    g_create_error = "device index out of range";
+    return nullptr;
+  }
+  if (!cuda_ok(nullptr, cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+  cudaDeviceProp prop;
+  if (!cuda_ok(nullptr, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return nullptr;
+  if (prop.major < 10) {
+    g_create_error = "libphos_cuda is built for sm_100a (B200) only";
+    return nullptr;
+  }
+  phos_ctx* ctx = new phos_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (options) ctx->opt = *options;
+  else ctx->opt = phos_options{16, 16, 9};
+  bool ok = cuda_ok(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  for (int i = 0; ok && i < kPipe; ++i)
+    ok = cuda_ok(nullptr, cudaStreamCreateWithFlags(&ctx->pipe[i].stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  ok = ok && cuda_ok(nullptr, cudaEventCreate(&ctx->ev_begin), "cudaEventCreate") &&
+       cuda_ok(nullptr, cudaEventCreate(&ctx->ev_end), "cudaEventCreate") &&
+       cuda_ok(nullptr, cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long)), "cudaMalloc(counters)") &&
+       cuda_ok(nullptr, cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long)), "cudaMemset(counters)");
+  int blocks = 0;
+  ok = ok && cuda_ok(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, trace_kernel<false>, kTraceBlock, 0),
+                     "occupancy(trace_kernel)");
+  if (!ok) {
+    phos_cuda_destroy(ctx);
+    return nullptr;
+  }
+  ctx->trace_blocks_per_sm = std::max(1, blocks);
+  return ctx;
+}
+
+void phos_cuda_destroy(phos_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < kPipe; ++i) {
+    free_rays(ctx->pipe[i].rays);
+    if (ctx->pipe[i].stream) cudaStreamDestroy(ctx->pipe[i].stream);
+  }
+  phos_render_release(ctx);
+  if (ctx->d_nodes) cudaFree(ctx->d_nodes);
+  if (ctx->d_tris) cudaFree(ctx->d_tris);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int phos_cuda_upload_accel(phos_ctx* ctx, const void* nodes288, uint32_t n_nodes, const void* packets384,
+                           uint32_t n_packets) {
+  if (!ctx) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  PackedAccel packed;
+  std::string err;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (!repack_accel((const RefNode*)nodes288, n_nodes, (const RefPacket*)packets384, n_packets, packed, err))
+    return fail(ctx, PHOS_ERR_ACCEL, err.c_str());
+  if (packed.max_depth + 2 > (uint32_t)(kSmemStack + kSpillStack))
+    return fail(ctx, PHOS_ERR_ACCEL, "tree deeper than the traversal stack");
+  const auto t1 = std::chrono::steady_clock::now();
+  cudaDeviceSynchronize();
+  if (ctx->d_nodes) cudaFree(ctx->d_nodes);
+  if (ctx->d_tris) cudaFree(ctx->d_tris);
+  ctx->d_nodes = ctx->d_tris = nullptr;
+  ctx->has_accel = false;
+  const size_t bn = packed.nodes.size() * sizeof(GNode), bt = packed.tris.size() * sizeof(GTri);
+  if (!cuda_ok(ctx, cudaMalloc(&ctx->d_nodes, bn), "cudaMalloc(nodes)") ||
+      !cuda_ok(ctx, cudaMalloc(&ctx->d_tris, bt), "cudaMalloc(triangles)") ||
+      !cuda_ok(ctx, cudaMemcpy(ctx->d_nodes, packed.nodes.data(), bn, cudaMemcpyHostToDevice), "upload nodes") ||
+      !cuda_ok(ctx, cudaMemcpy(ctx->d_tris, packed.tris.data(), bt, cudaMemcpyHostToDevice), "upload triangles"))
+    return PHOS_ERR_CUDA;
+  const auto t2 = std::chrono::steady_clock::now();
+  phos_accel_stats& s = ctx->stats;
+  s.ref_nodes = n_nodes;
+  s.ref_packets = n_packets;
+  s.nodes = (uint32_t)packed.nodes.size();
+  s.triangles = (uint32_t)packed.tris.size();
+  s.max_depth = packed.max_depth;
+  s.max_leaf_triangles = packed.max_leaf_tris;
+  s.bytes_nodes = bn;
+  s.bytes_triangles = bt;
+  s.repack_seconds = std::chrono::duration<double>(t1 - t0).count();
+  s.upload_seconds = std::chrono::duration<double>(t2 - t1).count();
+  ctx->has_accel = true;
+  return PHOS_OK;
+}
+
+int phos_cuda_accel_stats(phos_ctx* ctx, phos_accel_stats* out) {
+  if (!ctx || !out) return PHOS_ERR_INVALID;
+  if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "no acceleration structure uploaded");
+  *out = ctx->stats;
+  return PHOS_OK;
+}
+
+int phos_cuda_trace_device(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
+  if (!ctx || !rays) return PHOS_ERR_INVALID;
+  if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "trace before upload_accel");
+  cudaSetDevice(ctx->device);
+  return launch_trace(ctx, *rays, n, ctx->stream, ctx->d_counters + 8, false);
+}
+
+int phos_cuda_trace_count(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint64_t* out_nodes, uint64_t* out_tris) {
+  if (!ctx || !rays) return PHOS_ERR_INVALID;
+  if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "trace before upload_accel");
+  cudaSetDevice(ctx->device);
+  if (!cuda_ok(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream), "memset")) return PHOS_ERR_CUDA;
+  const int rc = launch_trace(ctx, *rays, n, ctx->stream, ctx->d_counters + 8, true);
+  if (rc) return rc;
+  unsigned long long c[2];
+  if (!cuda_ok(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream), "read counters") ||
+      !cuda_ok(ctx, cudaStreamSynchronize(ctx->stream), "sync"))
+    return PHOS_ERR_CUDA;
+  if (out_nodes) *out_nodes = c[0];
+  if (out_tris) *out_tris = c[1];
+  return PHOS_OK;
+}
+
+// Host-pointer trace: the stream is cut into chunks that flow through kPipe lanes, each lane
+// (its own CUDA stream and device staging stream) doing H2D -> trace -> D2H, so the copies of one
+// chunk overlap the traversal of another.
+int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
+  if (!ctx || !rays) return PHOS_ERR_INVALID;
+  if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "trace before upload_accel");
+  if (n == 0) return PHOS_OK;
+  cudaSetDevice(ctx->device);
+  const uint64_t chunk = std::min<uint64_t>(kPipeChunk, std::max<uint64_t>(32768, (n + kPipe - 1) / kPipe));
+  for (int i = 0; i < kPipe; ++i) {
+    if (ctx->pipe[i].capacity < chunk) {
+      cudaStreamSynchronize(ctx->pipe[i].stream);
+      free_rays(ctx->pipe[i].rays);
+      ctx->pipe[i].capacity = 0;
+      if (!alloc_rays(ctx, chunk, ctx->pipe[i].rays)) return PHOS_ERR_CUDA;
+      ctx->pipe[i].capacity = chunk;
+    }
+  }
+  int lane = 0;
+  for (uint64_t base = 0; base < n; base += chunk, lane = (lane + 1) % kPipe) {
+    const uint64_t cnt = std::min(chunk, n - base);
+    PipeLane& L = ctx->pipe[lane];
+    for (int k = 0; k < 12; ++k) {
+      const char* src = (const char*)in_ptr(*rays, k) + base * 4;
+      if (!cuda_ok(ctx, cudaMemcpyAsync((void*)in_ptr(L.rays, k), src, cnt * 4, cudaMemcpyHostToDevice, L.stream), "H2D rays"))
+        return PHOS_ERR_CUDA;
+    }
+    const int rc = launch_trace(ctx, L.rays, cnt, L.stream, ctx->d_counters + 16 + lane, false);
+    if (rc) return rc;
+    for (int k = 0; k < 6; ++k) {
+      char* dst = (char*)out_ptr(*rays, k) + base * 4;
+      if (!cuda_ok(ctx, cudaMemcpyAsync(dst, out_ptr(L.rays, k), cnt * 4, cudaMemcpyDeviceToHost, L.stream), "D2H rays"))
+        return PHOS_ERR_CUDA;
+    }
+  }
+  for (int i = 0; i < kPipe; ++i)
+    if (!cuda_ok(ctx, cudaStreamSynchronize(ctx->pipe[i].stream), "trace pipeline")) return PHOS_ERR_CUDA;
+  return PHOS_OK;
+}
+
+int phos_cuda_rays_alloc(phos_ctx* ctx, uint64_t n, phos_rays* out) {
+  if (!ctx || !out) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  memset(out, 0, sizeof(*out));
+  return alloc_rays(ctx, n, *out) ? PHOS_OK : PHOS_ERR_CUDA;
+}
+
+int phos_cuda_rays_free(phos_ctx* ctx, phos_rays* r) {
+  if (!ctx || !r) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_rays(*r);
+  return PHOS_OK;
+}
+
+int phos_cuda_rays_upload(phos_ctx* ctx, const phos_rays* host, const phos_rays* device, uint64_t n) {
+  if (!ctx || !host || !device) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  for (int k = 0; k < 12; ++k)
+    if (!cuda_ok(ctx, cudaMemcpyAsync((void*)in_ptr(*device, k), in_ptr(*host, k), n * 4, cudaMemcpyHostToDevice, ctx->stream),
+                 "rays_upload"))
+      return PHOS_ERR_CUDA;
+  return PHOS_OK;
+}
+
+int phos_cuda_rays_download(phos_ctx* ctx, const phos_rays* device, const phos_rays* host, uint64_t n) {
+  if (!ctx || !host || !device) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  for (int k = 0; k < 12; ++k)
+    if (!cuda_ok(ctx, cudaMemcpyAsync((void*)in_ptr(*host, k), in_ptr(*device, k), n * 4, cudaMemcpyDeviceToHost, ctx->stream),
+                 "rays_download"))
+      return PHOS_ERR_CUDA;
+  return cuda_ok(ctx, cudaStreamSynchronize(ctx->stream), "rays_download sync") ? PHOS_OK : PHOS_ERR_CUDA;
+}
+
+int phos_cuda_synchronize(phos_ctx* ctx) {
+  if (!ctx) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return cuda_ok(ctx, cudaStreamSynchronize(ctx->stream), "synchronize") ? PHOS_OK : PHOS_ERR_CUDA;
+}
+
+int phos_cuda_timer_begin(phos_ctx* ctx) {
+  if (!ctx) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return cuda_ok(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream), "timer_begin") ? PHOS_OK : PHOS_ERR_CUDA;
+}
+
+int phos_cuda_timer_end(phos_ctx* ctx, float* out_ms) {
+  if (!ctx || !out_ms) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (!cuda_ok(ctx, cudaEventRecord(ctx->ev_end, ctx->stream), "timer_end") ||
+      !cuda_ok(ctx, cudaEventSynchronize(ctx->ev_end), "timer_end sync") ||
+      !cuda_ok(ctx, cudaEventElapsedTime(out_ms, ctx->ev_begin, ctx->ev_end), "elapsed"))
+    return PHOS_ERR_CUDA;
+  return PHOS_OK;
+}
+
+uint64_t phos_cuda_launch_count(phos_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* phos_cuda_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void phos_cuda_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+"""The B200 device behind the renderer's device interface.
+
+Mirrors the reference's ``xpu_t`` (src/xpu.hpp:12-40) and its GPU slot ``cuda_t``
+(src/xpu/cuda.hpp:8-13): ``discover`` / ``make`` / ``preprocess`` / ``start`` / ``join`` keep their
+names, argument meaning and error behaviour (failures raise, as the reference throws
+``std::runtime_error``).  ``trace`` is the kernel functor the reference's tile renderer calls
+(``stream_mbvh_kernel_t::trace(rays, active)``, src/kernels/cpu/stream_bvh_kernel.hpp:19-25).
+Everything computes inside libphos_cuda.so; this file only moves pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import PhosAccelStats, PhosError, PhosOptions
+from .rays import PhosRays, RayBatch
+from .scene import Scene
+
+NODE_BYTES, PACKET_BYTES = 288, 384
+
+
+@dataclass
+class Options:
+    """parsed_options_t (src/options.hpp:6-43): the fields a device reads."""
+
+    samples_per_pixel: int = 16
+    paths_per_sample: int = 16
+    path_depth: int = 9
+    single_threaded: bool = False
+    host_only: bool = False
+
+
+class Accel:
+    """accel::mbvh_t (src/accel/bvh.hpp:17-49): the host-built 8-wide BVH in the reference's own
+    node (288 B) / packet (384 B) layout, produced by the library's host builder."""
+
+    def __init__(self, scene: Scene, threads: int = 0):
+        self._L = _lib.load()
+        d = scene.desc()
+        self._h = self._L.phos_bvh_build(C.byref(d), threads)
+        if not self._h:
+            raise PhosError("phos_bvh_build failed")
+        self.num_nodes = self._L.phos_bvh_num_nodes(self._h)
+        self.num_packets = self._L.phos_bvh_num_packets(self._h)
+        self.build_seconds = self._L.phos_bvh_build_seconds(self._h)
+
+    @property
+    def root(self) -> int:  # mbvh_t::root
+        return self._L.phos_bvh_nodes(self._h)
+
+    @property
+    def triangles(self) -> int:  # mbvh_t::triangles
+        return self._L.phos_bvh_packets(self._h)
+
+    def nodes_array(self) -> np.ndarray:
+        return np.ctypeslib.as_array(C.cast(self.root, C.POINTER(C.c_uint8)), (self.num_nodes * NODE_BYTES,)).copy()
+
+    def packets_array(self) -> np.ndarray:
+        return np.ctypeslib.as_array(C.cast(self.triangles, C.POINTER(C.c_uint8)), (self.num_packets * PACKET_BYTES,)).copy()
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.phos_bvh_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class DeviceRays:
+    """A ray stream resident in HBM (12 SoA arrays)."""
+
+    def __init__(self, dev: "CudaDevice", n: int):
+        self.dev, self.n = dev, int(n)
+        self.s = PhosRays()
+        dev._check(dev._L.phos_cuda_rays_alloc(dev._ctx, self.n, C.byref(self.s)))
+
+    def upload(self, host: RayBatch):
+        assert host.n == self.n
+        hs = host.as_struct()
+        self.dev._check(self.dev._L.phos_cuda_rays_upload(self.dev._ctx, C.byref(hs), C.byref(self.s), self.n))
+
+    def download(self, host: RayBatch | None = None) -> RayBatch:
+        host = host if host is not None else RayBatch(self.n)
+        hs = host.as_struct()
+        self.dev._check(self.dev._L.phos_cuda_rays_download(self.dev._ctx, C.byref(self.s), C.byref(hs), self.n))
+        return host
+
+    def free(self):
+        if self.s.px:
+            self.dev._L.phos_cuda_rays_free(self.dev._ctx, C.byref(self.s))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CudaDevice:
+    """cuda_t : xpu_t — one B200."""
+
+    def __init__(self, options: Options, device: int = 0):
+        self._L = _lib.load()
+        self.options = options
+        self.device = device
+        o = PhosOptions(options.samples_per_pixel, options.paths_per_sample, options.path_depth)
+        self._ctx = self._L.phos_cuda_create(device, C.byref(o))
+        if not self._ctx:
+            raise PhosError(self._L.phos_cuda_last_error(None).decode())
+        self.accel = None
+
+    # ---- xpu_t -----------------------------------------------------------------------------------
+    @staticmethod
+    def discover(options: Options) -> list["CudaDevice"]:
+        """xpu_t::discover (src/xpu.cpp:7-9): one device per visible GPU; empty under host_only."""
+        if options.host_only:
+            return []
+        return [CudaDevice.make(options, i) for i in range(_lib.load().phos_cuda_device_count())]
+
+    @staticmethod
+    def make(options: Options, device: int = 0) -> "CudaDevice":
+        return CudaDevice(options, device)
+
+    def preprocess(self, scene: Scene, accel: Accel | None = None) -> None:
+        """cpu_t::preprocess (src/xpu/cpu.cpp:219-221 -> details_t::reset :35-44): build the 8-wide
+        BVH on the host, then re-pack and upload it once."""
+        self.accel = accel if accel is not None else Accel(scene)
+        self.upload_accel(self.accel.root, self.accel.num_nodes, self.accel.triangles, self.accel.num_packets)
+
+    def upload_accel(self, nodes, n_nodes: int, packets, n_packets: int) -> None:
+        """Upload mbvh_t::root / mbvh_t::triangles given as addresses or uint8 numpy arrays."""
+        if isinstance(nodes, np.ndarray):
+            self._keep = (nodes, packets)
+            nodes, packets = nodes.ctypes.data, packets.ctypes.data
+        self._check(self._L.phos_cuda_upload_accel(self._ctx, nodes, n_nodes, packets, n_packets))
+
+    def accel_stats(self) -> PhosAccelStats:
+        s = PhosAccelStats()
+        self._check(self._L.phos_cuda_accel_stats(self._ctx, C.byref(s)))
+        return s
+
+    # ---- the kernel functor ------------------------------------------------------------------------
+    def trace(self, rays: RayBatch) -> RayBatch:
+        """trace(rays, active) in place on a host ray stream (copies in, traces, copies out)."""
+        s = rays.as_struct()
+        self._check(self._L.phos_cuda_trace(self._ctx, C.byref(s), rays.n))
+        return rays
+
+    def trace_device(self, rays: DeviceRays) -> None:
+        self._check(self._L.phos_cuda_trace_device(self._ctx, C.byref(rays.s), rays.n))
+
+    def trace_count(self, rays: DeviceRays) -> tuple[int, int]:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.phos_cuda_trace_count(self._ctx, C.byref(rays.s), rays.n, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def device_rays(self, n: int) -> DeviceRays:
+        return DeviceRays(self, n)
+
+    def synchronize(self) -> None:
+        self._check(self._L.phos_cuda_synchronize(self._ctx))
+
+    def timer_begin(self) -> None:
+        self._check(self._L.phos_cuda_timer_begin(self._ctx))
+
+    def timer_end(self) -> float:
+        ms = C.c_float(0)
+        self._check(self._L.phos_cuda_timer_end(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self._L.phos_cuda_launch_count(self._ctx))
+
+    # ---- plumbing ------------------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise PhosError(f"libphos_cuda error {rc}: {self._L.phos_cuda_last_error(self._ctx).decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._L.phos_cuda_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pinned_ray_batch(n: int) -> RayBatch:
+    """A RayBatch whose arrays live in page-locked host memory (fast, truly asynchronous copies)."""
+    L = _lib.load()
+    r = RayBatch(0)
+    r.n = int(n)
+    stride = (n * 4 + 255) // 256 * 256
+    base = L.phos_cuda_host_alloc(max(stride, 256) * 12)
+    if not base:
+        raise PhosError("phos_cuda_host_alloc failed")
+    r._pinned = base
+    names_f = ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v")
+    names_u = ("mesh", "face", "flags")
+    for i, k in enumerate(names_f + names_u):
+        ct = C.c_float if k in names_f else C.c_uint32
+        arr = np.ctypeslib.as_array(C.cast(base + stride * i, C.POINTER(ct)), (n,))
+        setattr(r, k, arr)
+    return r

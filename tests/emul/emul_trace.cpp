@@ -1,0 +1,79 @@
+// TEST INFRASTRUCTURE ONLY.  Host emulation of the device traversal function.
+//
+// Compiles phosphorus_mk2_b200/csrc/trace_ray.cuh — the exact source the CUDA kernel runs — for the
+// host by mapping the handful of CUDA intrinsics it uses onto libm / compiler builtins, and links it
+// with the product's own re-pack (repack.cpp).  This lets the CPU test suite (`-m "not gpu"`) check
+// the packed layout and the traversal logic against the oracle without a GPU.  It is never part of
+// the product: libphos_cuda.so does not contain it and no product module loads it.
+#include <cuda_runtime.h>  // vector types only
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline uint4 __ldg(const uint4* p) { return *p; }
+
+#include "../../phosphorus_mk2_b200/csrc/phos_internal.hpp"
+#include "../../phosphorus_mk2_b200/csrc/trace_ray.cuh"
+
+extern "C" {
+
+// returns 0 on success; err (>= 256 bytes) receives the re-pack error text otherwise
+int emul_trace(const void* nodes288, uint32_t n_nodes, const void* packets384, uint32_t n_packets, const phos_rays* rays,
+               uint64_t n, uint64_t* out_nodes, uint64_t* out_tris, uint32_t* out_stats /*4*/, char* err) {
+  using namespace phos;
+  PackedAccel packed;
+  std::string e;
+  if (!repack_accel((const RefNode*)nodes288, n_nodes, (const RefPacket*)packets384, n_packets, packed, e)) {
+    if (err) strncpy(err, e.c_str(), 255);
+    return 1;
+  }
+  if (out_stats) {
+    out_stats[0] = (uint32_t)packed.nodes.size();
+    out_stats[1] = (uint32_t)packed.tris.size();
+    out_stats[2] = packed.max_depth;
+    out_stats[3] = packed.max_leaf_tris;
+  }
+  DevAccel A;
+  A.nodes = (const uint4*)packed.nodes.data();
+  A.tris = (const uint4*)packed.tris.data();
+  static uint2 column[kSmemStack * kTraceBlock];
+  Stack st;
+  st.smem = column;
+  uint32_t nn = 0, nt = 0;
+  uint64_t tn = 0, tt = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    Ray r;
+    r.flags = rays->flags[i];
+    if (r.flags & PHOS_MASKED) continue;
+    r.ox = rays->px[i]; r.oy = rays->py[i]; r.oz = rays->pz[i];
+    r.wx = rays->wx[i]; r.wy = rays->wy[i]; r.wz = rays->wz[i];
+    r.d = rays->d[i];
+    r.order = 0xffffffffu;
+    r.mesh = r.face = 0u;
+    r.u = r.v = 0.0f;
+    nn = nt = 0;
+    if (trace_ray<true>(A, r, st, &nn, &nt)) {
+      rays->d[i] = r.d;
+      rays->flags[i] = r.flags;
+      if (!(r.flags & PHOS_SHADOW)) {
+        rays->mesh[i] = r.mesh; rays->face[i] = r.face; rays->u[i] = r.u; rays->v[i] = r.v;
+      }
+    }
+    tn += nn;
+    tt += nt;
+  }
+  if (out_nodes) *out_nodes = tn;
+  if (out_tris) *out_tris = tt;
+  return 0;
+}
+}
