@@ -135,6 +135,22 @@ int phos_cuda_trace_count(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint
 void* phos_cuda_host_alloc(uint64_t bytes);
 void  phos_cuda_host_free(void* p);
 
+/* Write a 256 MiB scratch buffer on the ctx stream so the 126 MB L2 holds none of the caller's data
+ * (timing hygiene between benchmark iterations). */
+int phos_cuda_flush_l2(phos_ctx* ctx);
+
+/* ---- scene and frame pipeline ------------------------------------------------------------------ */
+/* Upload what tile_renderer_t reads from scene_t while rendering (src/xpu/cpu.cpp:85-99): camera,
+ * and for the path tracer meshes, materials, lights.  Pinhole cameras only. */
+int phos_cuda_upload_scene(phos_ctx* ctx, const phos_scene_desc* scene);
+
+/* camera::perspective_kernel_t (src/kernels/cpu/camera.hpp:78-159): primary rays of every pixel of
+ * the given tiles for one film jitter (jx, jy) shared by the whole sample, into device ray arrays.
+ * The rays of tile k start at slot sum_{j<k} w_j * h_j, row-major inside the tile (slot = y * w + x,
+ * src/xpu/cpu.cpp:177); unlike the reference, partial tiles are not padded to 1024 slots. */
+int phos_cuda_camera_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, float jx, float jy,
+                          const phos_rays* device_rays);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,8 @@ struct phos_ctx {
   uint64_t launches = 0;
   phos::PipeLane pipe[phos::kPipe];
   phos::RenderState* render = nullptr;
+  void* d_flush = nullptr;  // L2 flush scratch (bench hygiene)
+  int flush_value = 0;
 };
 
 namespace phos {

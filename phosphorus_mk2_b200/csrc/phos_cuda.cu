@@ -152,6 +152,7 @@ void phos_cuda_destroy(phos_ctx* ctx) {
   if (ctx->d_nodes) cudaFree(ctx->d_nodes);
   if (ctx->d_tris) cudaFree(ctx->d_tris);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_flush) cudaFree(ctx->d_flush);
   if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

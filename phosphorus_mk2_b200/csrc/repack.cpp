@@ -245,18 +245,26 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
     // ---- quantisation grid -----------------------------------------------------------------------
     GNode g;
     memset(&g, 0, sizeof(g));
-    const float origin[3] = {(float)nb.lo[0], (float)nb.lo[1], (float)nb.lo[2]};
+    // margin, in grid cells, swallowing the traversal's fp32 error in fma(q, idir*2^e, (o-org)*idir)
+    // for rays that start inside or near the node: at most ~10 * 2^-24 * 255 cells of plane shift
+    // (DESIGN.md "conservative traversal").  The grid origin sits 2 margins below the true minimum
+    // so the lowest plane keeps its margin too (q cannot go below 0).
+    const double margin = 1.0 / 1024.0;
     double o[3], scale[3];
     uint8_t ebyte[3];
     for (int a = 0; a < 3; ++a) {
-      // fp32 origin at or below the true minimum
-      float of = origin[a];
-      if ((double)of > nb.lo[a]) of = std::nextafterf(of, -FLT_MAX);
-      o[a] = of;
-      const double ext = nb.hi[a] - o[a];
-      int e = ext > 0.0 ? (int)std::ceil(std::log2(ext / 253.0)) : -126;
+      const double ext0 = nb.hi[a] - nb.lo[a];
+      int e = ext0 > 0.0 ? (int)std::ceil(std::log2(ext0 / 252.0)) : -126;
       e = std::max(-126, std::min(126, e));
-      while (std::ldexp(253.0, e) < ext && e < 126) ++e;
+      float of = 0.0f;
+      for (;; ++e) {
+        const double sc = std::ldexp(1.0, e);
+        const double want = nb.lo[a] - 2.0 * margin * sc;
+        of = (float)want;
+        if ((double)of > want) of = std::nextafterf(of, -FLT_MAX);  // fp32 origin at or below the wanted one
+        if ((nb.hi[a] - (double)of) / sc + 2.0 * margin <= 254.0 || e >= 126) break;
+      }
+      o[a] = of;
       scale[a] = std::ldexp(1.0, e);
       ebyte[a] = (uint8_t)(e + 127);
       (&g.ox)[a] = of;
@@ -265,9 +273,6 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
     g.ey = ebyte[1];
     g.ez = ebyte[2];
 
-    // margin, in grid cells, swallowing the traversal's fp32 error in fma(q, idir*2^e, (o-org)*idir):
-    // at most 2^-23 * 255 cells of plane shift (see DESIGN.md "conservative traversal")
-    const double margin = 1.0 / 1024.0;
     uint8_t* qlo[3] = {g.qlox, g.qloy, g.qloz};
     uint8_t* qhi[3] = {g.qhix, g.qhiy, g.qhiz};
     for (int s = 0; s < 8; ++s) {
@@ -287,9 +292,8 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
       for (int a = 0; a < 3; ++a) {
         double ql = std::floor((c.box.lo[a] - o[a]) / scale[a] - margin);
         double qh = std::ceil((c.box.hi[a] - o[a]) / scale[a] + margin);
-        ql = std::max(0.0, std::min(255.0, ql));
-        qh = std::max(0.0, std::min(255.0, qh));
-        if (o[a] + ql * scale[a] > c.box.lo[a] || o[a] + qh * scale[a] < c.box.hi[a]) {
+        if (ql < 0.0 || qh > 255.0 || o[a] + (ql + margin) * scale[a] > c.box.lo[a] ||
+            o[a] + (qh - margin) * scale[a] < c.box.hi[a]) {
           err = "internal: quantised box does not contain the child box";
           return false;
         }

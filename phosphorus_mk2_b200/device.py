@@ -15,7 +15,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import lib as _lib
-from .lib import PhosAccelStats, PhosError, PhosOptions
+from .lib import PhosAccelStats, PhosError, PhosOptions, PhosTile
 from .rays import PhosRays, RayBatch
 from .scene import Scene
 
@@ -31,6 +31,23 @@ class Options:
     path_depth: int = 9
     single_threaded: bool = False
     host_only: bool = False
+
+
+def make_tiles(width: int, height: int, tile_size: int = 32) -> list[tuple[int, int, int, int]]:
+    """job::tiles_t::make (src/jobs/tiles.hpp:49-89): row-major list of (x, y, w, h), partial tiles
+    on the right / bottom edges."""
+    out = []
+    for y in range(0, height, tile_size):
+        for x in range(0, width, tile_size):
+            out.append((x, y, min(tile_size, width - x), min(tile_size, height - y)))
+    return out
+
+
+def tile_array(tiles) -> "C.Array":
+    arr = (PhosTile * len(tiles))()
+    for i, (x, y, w, h) in enumerate(tiles):
+        arr[i].x, arr[i].y, arr[i].w, arr[i].h = x, y, w, h
+    return arr
 
 
 class Accel:
@@ -157,6 +174,19 @@ class CudaDevice:
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._check(self._L.phos_cuda_trace_count(self._ctx, C.byref(rays.s), rays.n, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def upload_scene(self, scene: Scene) -> None:
+        d = scene.desc()
+        self._check(self._L.phos_cuda_upload_scene(self._ctx, C.byref(d)))
+
+    def camera_rays(self, tiles, rays: DeviceRays, jx: float = 0.5, jy: float = 0.5) -> None:
+        """camera::perspective_kernel_t over a list of (x, y, w, h) tiles into a device stream."""
+        arr = tile_array(tiles)
+        assert sum(t[2] * t[3] for t in tiles) <= rays.n
+        self._check(self._L.phos_cuda_camera_rays(self._ctx, arr, len(tiles), jx, jy, C.byref(rays.s)))
+
+    def flush_l2(self) -> None:
+        self._check(self._L.phos_cuda_flush_l2(self._ctx))
 
     def device_rays(self, n: int) -> DeviceRays:
         return DeviceRays(self, n)

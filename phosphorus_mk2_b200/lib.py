@@ -70,6 +70,9 @@ SYMBOLS = {
     "phos_cuda_launch_count": (_U64, [_VP]),
     "phos_cuda_host_alloc": (_VP, [_U64]),
     "phos_cuda_host_free": (None, [_VP]),
+    "phos_cuda_flush_l2": (_I, [_VP]),
+    "phos_cuda_upload_scene": (_I, [_VP, C.POINTER(PhosSceneDesc)]),
+    "phos_cuda_camera_rays": (_I, [_VP, C.POINTER(PhosTile), _U32, C.c_float, C.c_float, _RP]),
 }
 
 _lib = None

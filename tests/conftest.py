@@ -1,0 +1,68 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_gpu() -> bool:
+    try:
+        from phosphorus_mk2_b200 import lib
+        return lib.load().phos_cuda_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m gpu` on a box without a GPU must fail loudly, not skip: the product has no CPU path.
+    pass
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle.pyoracle import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def reflib():
+    """The reference's own compiled hot path (oracle/_ref); absent only if never built."""
+    from oracle.pyoracle import RefLib
+    if not RefLib.available():
+        pytest.skip("oracle/_ref/libphos_ref.so not built (needs /root/reference at build time)")
+    return RefLib()
+
+
+@pytest.fixture(scope="session")
+def emul():
+    """Host emulation of the device traversal source (tests/emul), built on demand."""
+    import ctypes as C
+    from phosphorus_mk2_b200.rays import PhosRays
+    here = os.path.join(ROOT, "tests", "emul")
+    so = os.path.join(here, "libemul_trace.so")
+    srcs = [os.path.join(here, "emul_trace.cpp"), os.path.join(ROOT, "phosphorus_mk2_b200", "csrc", "repack.cpp")]
+    deps = srcs + [os.path.join(ROOT, "phosphorus_mk2_b200", "csrc", f) for f in ("trace_ray.cuh", "phos_internal.hpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+                        "-I/usr/local/cuda/include", *srcs, "-o", so], check=True)
+    L = C.CDLL(so)
+    L.emul_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(PhosRays), C.c_uint64,
+                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_char_p]
+    return L
+
+
+@pytest.fixture(scope="session")
+def device():
+    """One CudaDevice on cuda:0.  Raises (does not skip) when the library or the GPU is missing."""
+    from phosphorus_mk2_b200.device import CudaDevice, Options
+    dev = CudaDevice.make(Options(), 0)
+    yield dev
+    dev.close()

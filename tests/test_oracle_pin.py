@@ -1,0 +1,81 @@
+"""The oracle's pin: the plain-C restatement (oracle/phos_oracle.c) against vectors produced by the
+reference's own compiled kernels (tests/golden/make_golden.py), and — when oracle/_ref is present —
+against the reference library live.  CPU only."""
+import numpy as np
+import pytest
+
+from parity import BATCHES, CASES, classify_vs_stream, golden_out, golden_rays, load_golden, mismatches
+from phosphorus_mk2_b200 import raysets, scenes
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("batch", BATCHES)
+def test_brute_force_equals_reference_linear_kernel(oracle, case, batch):
+    z = load_golden(case)
+    rays = golden_rays(z, batch)
+    want = golden_out(z, batch, "linear", rays)
+    got = oracle.brute_force(z["packets"], rays)
+    # brute force is order-identical to the reference's linear kernel: every field, every ray, bit-exact
+    for f in ("d", "u", "v", "mesh", "face", "flags"):
+        assert np.array_equal(getattr(got, f).view(np.uint32), getattr(want, f).view(np.uint32)), f
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("batch", BATCHES)
+def test_traversal_equals_brute_force(oracle, case, batch):
+    z = load_golden(case)
+    rays = golden_rays(z, batch)
+    want = golden_out(z, batch, "linear", rays)
+    got, cnt = oracle.traverse(z["nodes"], z["packets"], rays)
+    assert len(mismatches(rays, got, want)) == 0
+    assert cnt.rays == int(((rays.flags & 2) == 0).sum())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_stream_kernel_disagreements_are_reference_false_misses_or_ties(case):
+    """The reference's stream kernel (approximate rcpps slab test) may miss hits or return a farther
+    triangle; it never finds a hit the exact kernel does not."""
+    z = load_golden(case)
+    for batch in ("aimed", "random", "special"):
+        rays = golden_rays(z, batch)
+        lin = golden_out(z, batch, "linear", rays)
+        st = golden_out(z, batch, "stream", rays)
+        missed, farther, tied, other = classify_vs_stream(rays, st, lin)
+        assert len(other) == 0
+        if batch != "special":  # the special batch aims at vertices and edges on purpose: ties abound
+            assert len(missed) + len(farther) + len(tied) <= 0.01 * rays.n
+
+
+def test_live_reference_agrees_with_oracle(oracle, reflib):
+    """Fresh (non-golden) case against the compiled reference, when it is present."""
+    sc = scenes.heightfield(40, seed=5)
+    rs = reflib.scene(sc)
+    rs.build()
+    nodes, packets = rs.accel()
+    rays = raysets.aimed_rays(sc, 3000, seed=21)
+    lin, _ = rs.trace(rays, "linear")
+    got = oracle.brute_force(packets, rays)
+    for f in ("d", "u", "v", "mesh", "face", "flags"):
+        assert np.array_equal(getattr(got, f).view(np.uint32), getattr(lin, f).view(np.uint32)), f
+    trav, _ = oracle.traverse(nodes, packets, rays)
+    assert len(mismatches(rays, trav, lin)) == 0
+
+
+def test_camera_rays_match_reference_render_geometry(oracle):
+    """orc_camera_rays: centre pixel looks down -z of the camera; corner rays span the stated fov."""
+    sc = scenes.cornell_box(64, 64)
+    r = oracle.camera_rays(sc.camera, jx=0.5, jy=0.5)
+    assert r.n == 64 * 64
+    n = np.sqrt(r.wx ** 2 + r.wy ** 2 + r.wz ** 2)
+    assert np.allclose(n, 1.0, atol=2e-7)
+    assert np.all(r.pz == np.float32(3.8)) and np.all(r.py == np.float32(1.0))
+    # pixel (x, y): d = ((x - .5)/W - .5 + jx/W) * (W/H) * zoom, (.5 - (y - .5)/H + jy/H) * zoom, -1)
+    # (camera.hpp:124-133; note the film jitter moves +y although pixel rows grow downwards)
+    import math
+    zoom = 1.12 * math.tan(sc.camera.fov * 0.5)
+    for (x, y) in ((32, 32), (0, 0), (63, 17)):
+        dx = ((x - 0.5) / 64 - 0.5 + 0.5 / 64) * zoom
+        dy = (0.5 - (y - 0.5) / 64 + 0.5 / 64) * zoom
+        l = math.sqrt(dx * dx + dy * dy + 1.0)
+        k = y * 64 + x
+        assert abs(r.wx[k] - dx / l) < 1e-6 and abs(r.wy[k] - dy / l) < 1e-6 and abs(r.wz[k] + 1.0 / l) < 1e-6
