@@ -74,7 +74,9 @@ int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t s
   a.cursor = cursor;
   a.counters = ctx->d_counters;
   if (!cuda_ok(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream), "memset(cursor)")) return PHOS_ERR_CUDA;
-  const uint64_t want = (n + kTraceBlock - 1) / kTraceBlock;
+  a.tma_ok = 1;  // TMA bulk copies need 16-byte aligned sources
+  for (int k = 0; k < 8; ++k) a.tma_ok &= ((uintptr_t)in_ptr(dev, k) & 15u) == 0;
+  const uint64_t want = (n + (uint64_t)kChunk * kTraceWarps - 1) / ((uint64_t)kChunk * kTraceWarps);
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * ctx->trace_blocks_per_sm);
   if (count) trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(a);
   else trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(a);

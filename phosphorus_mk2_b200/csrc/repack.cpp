@@ -245,27 +245,30 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
     // ---- quantisation grid -----------------------------------------------------------------------
     GNode g;
     memset(&g, 0, sizeof(g));
-    // margin, in grid cells, swallowing the traversal's fp32 error in fma(q, idir*2^e, (o-org)*idir)
-    // for rays that start inside or near the node: at most ~10 * 2^-24 * 255 cells of plane shift
-    // (DESIGN.md "conservative traversal").  The grid origin sits 2 margins below the true minimum
-    // so the lowest plane keeps its margin too (q cannot go below 0).
-    const double margin = 1.0 / 1024.0;
+    // Plane q of an axis sits at og + (2^15 + q) * 2^e: the kernel decodes a byte with one PRMT into
+    // the float m = 1 + q * 2^-15 (bits 0x3F800000 | q << 8) and evaluates t = fma(m, 2^(e+15) / dir,
+    // (og - org) / dir).  `og` is the stored fp32 origin, 2^15 cells below the grid.
+    // margin, in grid cells, swallows the fp32 error of that formulation for rays that start inside or
+    // near the node: the rounding of (og - org) / dir is worth <= ~2^-8 cells (DESIGN.md "conservative
+    // traversal"); rays far from the node are covered by the relative slack in the kernel.  The grid
+    // starts 2 margins below the true minimum so the lowest plane keeps its margin (q >= 0).
+    const double margin = 1.0 / 64.0;
     double o[3], scale[3];
     uint8_t ebyte[3];
     for (int a = 0; a < 3; ++a) {
       const double ext0 = nb.hi[a] - nb.lo[a];
-      int e = ext0 > 0.0 ? (int)std::ceil(std::log2(ext0 / 252.0)) : -126;
-      e = std::max(-126, std::min(126, e));
+      int e = ext0 > 0.0 ? (int)std::ceil(std::log2(ext0 / 252.0)) : -100;
+      e = std::max(-100, std::min(100, e));
       float of = 0.0f;
       for (;; ++e) {
         const double sc = std::ldexp(1.0, e);
-        const double want = nb.lo[a] - 2.0 * margin * sc;
+        const double want = nb.lo[a] - 2.0 * margin * sc - 32768.0 * sc;
         of = (float)want;
         if ((double)of > want) of = std::nextafterf(of, -FLT_MAX);  // fp32 origin at or below the wanted one
-        if ((nb.hi[a] - (double)of) / sc + 2.0 * margin <= 254.0 || e >= 126) break;
+        if ((nb.hi[a] - ((double)of + 32768.0 * sc)) / sc + 2.0 * margin <= 254.0 || e >= 100) break;
       }
-      o[a] = of;
       scale[a] = std::ldexp(1.0, e);
+      o[a] = (double)of + 32768.0 * scale[a];
       ebyte[a] = (uint8_t)(e + 127);
       (&g.ox)[a] = of;
     }

@@ -1,55 +1,239 @@
-// trace.cuh — the ray-query kernel: persistent CTAs draining a ray stream through trace_ray()
-// (trace_ray.cuh holds the traversal and the triangle test).
+// trace.cuh — the ray-query kernel (sm_100a): persistent warps that drain a ray stream through the
+// node / triangle steps of trace_ray.cuh.
+//
+//   * work distribution: every warp claims 64-ray chunks of the stream from one global cursor; the
+//     chunk's eight input arrays (p, wi, d, flags) are staged into shared memory with TMA bulk copies
+//     (cp.async.bulk + mbarrier), double-buffered so the next chunk lands while the current one is
+//     being traversed; a partial tail chunk (or a misaligned stream) is staged with plain loads;
+//   * per-lane refill: a lane whose ray is finished writes its hit record and takes the next ray of
+//     the warp's chunk as soon as enough lanes are idle (ballot + popc ranks, no atomics), so a long
+//     ray never holds 31 finished lanes hostage;
+//   * warp-voted phases: each iteration the warp either runs one node step (8 quantised child boxes)
+//     for the lanes that need one, or one Möller–Trumbore step for the lanes with pending leaf
+//     triangles — whichever more lanes want — so both inner loops run converged instead of every
+//     lane dragging the warp through its own leaf loop;
+//   * traversal stack: kSmemStack entries per ray in shared memory ([entry][thread], conflict-free),
+//     deeper entries in a local-memory spill that ordinary trees never touch.
 #pragma once
 #include "trace_ray.cuh"
 
 namespace phos {
 
+constexpr int kChunk = 64;      // rays per claimed chunk
+constexpr int kRefillMin = 6;   // idle lanes that trigger a refill
+constexpr int kTraceWarps = kTraceBlock / 32;
+
 struct TraceArgs {
   phos_rays rays;  // device pointers
   unsigned long long n;
   DevAccel accel;
-  unsigned long long* cursor;    // work counter (zeroed before launch)
+  unsigned long long* cursor;    // chunk counter (zeroed before launch)
   unsigned long long* counters;  // [2]: nodes visited, triangles tested (kCount only)
+  int tma_ok;                    // all eight input arrays are 16-byte aligned
 };
 
-// Persistent CTAs: every warp pulls 32 consecutive rays at a time from a global cursor until the
-// stream is drained, so long rays do not hold back a whole CTA's worth of the stream.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 template <bool kCount>
 __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs P) {
   __shared__ uint2 s_stack[kSmemStack * kTraceBlock];
+  __shared__ alignas(128) uint32_t s_stage[kTraceWarps][2][8][kChunk];
+  __shared__ alignas(8) unsigned long long s_bar[kTraceWarps][2];
+
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint32_t(*stage)[8][kChunk] = s_stage[warp];
+  unsigned long long* bar = s_bar[warp];
+  if (lane == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  const uint32_t* src[8] = {(const uint32_t*)P.rays.px, (const uint32_t*)P.rays.py, (const uint32_t*)P.rays.pz,
+                            (const uint32_t*)P.rays.wx, (const uint32_t*)P.rays.wy, (const uint32_t*)P.rays.wz,
+                            (const uint32_t*)P.rays.d,  (const uint32_t*)P.rays.flags};
+
+  // ---- the warp's view of the stream (all warp-uniform) ---------------------------------------------
+  uint32_t phase = 0;  // bit b: parity the next wait on buffer b expects
+  int cur_buf = 0;
+  unsigned long long cur_base = 0, nxt_base = 0;
+  uint32_t cur_cnt = 0, taken = 0, nxt_cnt = 0;
+  bool nxt_tma = false, exhausted = false;
+
+  auto claim = [&](int buf) {  // claim the next chunk of the stream and start staging it into `buf`
+    nxt_cnt = 0;
+    if (exhausted) return;
+    unsigned long long c = 0;
+    if (lane == 0) c = atomicAdd(P.cursor, 1ull);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    const unsigned long long base = c * kChunk;
+    if (base >= P.n) {
+      exhausted = true;
+      return;
+    }
+    nxt_base = base;
+    nxt_cnt = (uint32_t)min((unsigned long long)kChunk, P.n - base);
+    nxt_tma = P.tma_ok && nxt_cnt == kChunk;
+    if (nxt_tma) {
+      if (lane == 0) {
+        mbar_expect_tx(&bar[buf], 8u * kChunk * 4u);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) bulk_g2s(stage[buf][a], src[a] + base, kChunk * 4u, &bar[buf]);
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        for (uint32_t k = lane; k < nxt_cnt; k += 32) stage[buf][a][k] = src[a][base + k];
+    }
+    __syncwarp();
+  };
+  auto advance = [&]() -> bool {  // the staged chunk becomes current; prefetch the one after
+    if (nxt_cnt == 0) return false;
+    const int b = cur_buf ^ 1;
+    if (nxt_tma) {
+      mbar_wait(&bar[b], (phase >> b) & 1u);
+      phase ^= 1u << b;
+    }
+    cur_buf = b;
+    cur_base = nxt_base;
+    cur_cnt = nxt_cnt;
+    taken = 0;
+    __syncwarp();  // every lane is done reading the buffer we are about to refill
+    claim(b ^ 1);
+    return true;
+  };
+  claim(1);
+
+  // ---- per-lane traversal state ----------------------------------------------------------------------
   Stack st;
   st.smem = s_stack + threadIdx.x;
-  const unsigned lane = threadIdx.x & 31u;
+  st.sp = 0;
+  Ray r;
+  RayDir rd;
+  r.flags = 0;
+  rd.oct = 0;
+  unsigned long long ridx = 0;
+  bool has_ray = false, changed = false;
+  uint2 cur = make_uint2(0u, 0u);
+  uint32_t trem = 0, tptr = 0, lmask = 0, lcounts = 0, lbase = 0;
   uint32_t n_nodes = 0, n_tris = 0;
+
   for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(P.cursor, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= P.n) break;
-    const unsigned long long i = base + lane;
-    if (i >= P.n) continue;
-    Ray r;
-    r.flags = P.rays.flags[i];
-    if (r.flags & PHOS_MASKED) continue;
-    r.ox = P.rays.px[i];
-    r.oy = P.rays.py[i];
-    r.oz = P.rays.pz[i];
-    r.wx = P.rays.wx[i];
-    r.wy = P.rays.wy[i];
-    r.wz = P.rays.wz[i];
-    r.d = P.rays.d[i];
-    r.order = 0xffffffffu;
-    r.mesh = r.face = 0u;
-    r.u = r.v = 0.0f;
-    if (trace_ray<kCount>(P.accel, r, st, &n_nodes, &n_tris)) {
-      P.rays.d[i] = r.d;
-      P.rays.flags[i] = r.flags;
-      if (!(r.flags & PHOS_SHADOW)) {
-        P.rays.mesh[i] = r.mesh;
-        P.rays.face[i] = r.face;
-        P.rays.u[i] = r.u;
-        P.rays.v[i] = r.v;
+    // 1. retire finished rays
+    if (has_ray && (trem | lmask) == 0u && (cur.y >> 8) == 0u && st.sp == 0) {
+      if (changed) {
+        P.rays.d[ridx] = r.d;
+        P.rays.flags[ridx] = r.flags;
+        if (!(r.flags & PHOS_SHADOW)) {
+          P.rays.mesh[ridx] = r.mesh;
+          P.rays.face[ridx] = r.face;
+          P.rays.u[ridx] = r.u;
+          P.rays.v[ridx] = r.v;
+        }
+      }
+      has_ray = false;
+    }
+    // 2. refill idle lanes from the warp's chunk
+    unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+    if (__popc(idle) >= kRefillMin && (taken < cur_cnt || nxt_cnt != 0)) {
+      while (idle) {
+        if (taken == cur_cnt && !advance()) break;
+        const uint32_t rank = __popc(idle & lt_mask);
+        const uint32_t take = min((uint32_t)__popc(idle), cur_cnt - taken);
+        if (!has_ray && rank < take) {
+          const uint32_t k = taken + rank;
+          const uint32_t fl = stage[cur_buf][7][k];
+          if (!(fl & PHOS_MASKED)) {  // MASKED rays are consumed without being traced
+            r.ox = __uint_as_float(stage[cur_buf][0][k]);
+            r.oy = __uint_as_float(stage[cur_buf][1][k]);
+            r.oz = __uint_as_float(stage[cur_buf][2][k]);
+            r.wx = __uint_as_float(stage[cur_buf][3][k]);
+            r.wy = __uint_as_float(stage[cur_buf][4][k]);
+            r.wz = __uint_as_float(stage[cur_buf][5][k]);
+            r.d = __uint_as_float(stage[cur_buf][6][k]);
+            r.flags = fl;
+            r.order = 0xffffffffu;
+            r.mesh = r.face = 0u;
+            r.u = r.v = 0.0f;
+            rd = make_raydir(r.wx, r.wy, r.wz);
+            ridx = cur_base + k;
+            cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
+            st.sp = 0;
+            trem = lmask = 0u;
+            changed = false;
+            has_ray = true;
+          }
+        }
+        taken += take;
+        idle = __ballot_sync(0xffffffffu, !has_ray);
+      }
+    }
+    // 3. vote: node step or triangle step
+    const unsigned act = __ballot_sync(0xffffffffu, has_ray);
+    if (act == 0u) break;  // stream drained and every lane retired
+    const bool tri_work = has_ray && (trem | lmask) != 0u;
+    const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
+    if (__popc(tl) >= __popc(act & ~tl)) {
+      if (tri_work) {
+        if (trem == 0u) {  // open the next hit leaf, nearest octant first
+          const uint32_t slot = (__ffs(lmask) - 1) ^ rd.oct;
+          lmask &= lmask - 1u;
+          trem = (lcounts >> (4u * slot)) & 15u;  // 0 for an empty slot
+          tptr = lbase + nibble_prefix(lcounts, slot);
+        }
+        if (trem) {
+          const uint4* tp = P.accel.tris + 3ull * tptr;
+          const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+          ++tptr;
+          --trem;
+          if (kCount) ++n_tris;
+          float ds, us, vs;
+          if (mt_triangle(a, b, c, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) && accept_hit(r, ds, us, vs, c)) {
+            changed = true;
+            if (r.flags & PHOS_SHADOW) {  // any-hit: this ray is done
+              trem = lmask = 0u;
+              cur.y = 0u;
+              st.sp = 0;
+            }
+          }
+        }
+      }
+    } else if (has_ray && !tri_work) {
+      if ((cur.y >> 8) == 0u && st.sp != 0) cur = st.pop();
+      if (cur.y >> 8) {
+        const uint32_t node = take_child(cur, rd.oct);
+        if (cur.y >> 8) st.push(cur);
+        const NodeHits h = node_test(P.accel, node, r.ox, r.oy, r.oz, rd, r.d * PHOS_CULL_SLACK);
+        if (kCount) ++n_nodes;
+        lmask = h.leaf;
+        lcounts = h.counts;
+        lbase = h.tri_base;
+        cur = make_uint2(h.child_base, h.imask | (h.inner << 8));
       }
     }
   }

@@ -1,4 +1,5 @@
-// trace_ray.cuh — closest-hit / any-hit traversal of the packed 8-wide BVH + Möller–Trumbore (sm_100a).
+// trace_ray.cuh — the per-ray pieces of the ray-query path: Möller–Trumbore, the 8-wide node test
+// on the packed layout, the traversal stack and a plain one-ray traversal loop (sm_100a).
 //
 // Replaces stream_mbvh_kernel_t::trace (reference src/kernels/cpu/stream_bvh_kernel.cpp:17-161) and
 // moeller_trumbore_t<8>::iterate_rays / iterate_triangles (src/accel/triangle.hpp:125-287) for ray
@@ -26,11 +27,11 @@ struct DevAccel {
 };
 
 constexpr int kTraceBlock = 128;  // threads per CTA
-constexpr int kSmemStack = 24;    // traversal-stack entries per ray held in shared memory
-constexpr int kSpillStack = 72;   // further entries (local memory; only touched by trees deeper than kSmemStack)
+constexpr int kSmemStack = 16;    // traversal-stack entries per ray held in shared memory
+constexpr int kSpillStack = 80;   // further entries (local memory; only touched when the stack runs deeper)
 
 // relative slack of the slab test: covers the fp32 error of the fma plane formulation for rays far
-// from the node (<= 10 * 2^-24 relative, DESIGN.md "conservative traversal")
+// from the node (<= ~10 * 2^-24 relative, DESIGN.md "conservative traversal")
 #define PHOS_SLAB_SLACK 1.000003814697265625f /* 1 + 2^-18 */
 // relative slack of the distance cull: nodes are entered while t_near <= d * (1 + 2^-15), so a
 // triangle whose Möller–Trumbore distance undercuts the current best by rounding error is still seen
@@ -46,23 +47,42 @@ struct Ray {
   float u, v;
 };
 
+// per-ray constants of the slab test
+struct RayDir {
+  float idx, idy, idz;  // 1 / dir (IEEE); a zero / tiny component is treated as +-2^-60
+  uint32_t oct;         // bit a set <=> dir[a] < 0
+};
+
+__device__ __forceinline__ RayDir make_raydir(float wx, float wy, float wz) {
+  const float tiny = 8.67361737988403547e-19f;  // 2^-60: no 0 * inf can arise
+  const float dx = fabsf(wx) < tiny ? copysignf(tiny, wx) : wx;
+  const float dy = fabsf(wy) < tiny ? copysignf(tiny, wy) : wy;
+  const float dz = fabsf(wz) < tiny ? copysignf(tiny, wz) : wz;
+  RayDir r;
+  r.idx = __fdiv_rn(1.0f, dx);
+  r.idy = __fdiv_rn(1.0f, dy);
+  r.idz = __fdiv_rn(1.0f, dz);
+  r.oct = (r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u);
+  return r;
+}
+
 __device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
   // simd::vector3_t::dot (reference src/math/simd/vector.hpp:98-100): madd(x, x', madd(y, y', z * z'))
   return __fmaf_rn(ax, bx, __fmaf_rn(ay, by, __fmul_rn(az, bz)));
 }
 
-// One ray against one packed triangle.  Returns true when every mask of triangle.hpp:154-159 holds
-// against tmax (strict ds < tmax is applied by the caller together with the tie rule).
-__device__ __forceinline__ bool mt_triangle(const uint4 a, const uint4 b, const uint4 c, const Ray& r, float& ds,
-                                            float& us, float& vs) {
+// One ray against one packed triangle.  Returns true when the masks of triangle.hpp:154-159 hold,
+// except ds < d, which the caller applies together with the tie rule.
+__device__ __forceinline__ bool mt_triangle(const uint4 a, const uint4 b, const uint4 c, float ox, float oy, float oz,
+                                            float wx, float wy, float wz, float& ds, float& us, float& vs) {
   const float v0x = __uint_as_float(a.x), v0y = __uint_as_float(a.y), v0z = __uint_as_float(a.z);
   const float e0x = __uint_as_float(a.w), e0y = __uint_as_float(b.x), e0z = __uint_as_float(b.y);
   const float e1x = __uint_as_float(b.z), e1y = __uint_as_float(b.w), e1z = __uint_as_float(c.x);
-  const float tx = __fsub_rn(r.ox, v0x), ty = __fsub_rn(r.oy, v0y), tz = __fsub_rn(r.oz, v0z);
+  const float tx = __fsub_rn(ox, v0x), ty = __fsub_rn(oy, v0y), tz = __fsub_rn(oz, v0z);
   // p = wi x e1 ; cross = msub(a, b, c * d) (vector.hpp:102-109)
-  const float px = __fmaf_rn(r.wy, e1z, -__fmul_rn(r.wz, e1y));
-  const float py = __fmaf_rn(r.wz, e1x, -__fmul_rn(r.wx, e1z));
-  const float pz = __fmaf_rn(r.wx, e1y, -__fmul_rn(r.wy, e1x));
+  const float px = __fmaf_rn(wy, e1z, -__fmul_rn(wz, e1y));
+  const float py = __fmaf_rn(wz, e1x, -__fmul_rn(wx, e1z));
+  const float pz = __fmaf_rn(wx, e1y, -__fmul_rn(wy, e1x));
   const float det = dot3_rn(e0x, e0y, e0z, px, py, pz);
   const float ood = __fdiv_rn(1.0f, det);
   // q = t x e0
@@ -70,7 +90,7 @@ __device__ __forceinline__ bool mt_triangle(const uint4 a, const uint4 b, const 
   const float qy = __fmaf_rn(tz, e0x, -__fmul_rn(tx, e0z));
   const float qz = __fmaf_rn(tx, e0y, -__fmul_rn(ty, e0x));
   us = __fmul_rn(dot3_rn(tx, ty, tz, px, py, pz), ood);
-  vs = __fmul_rn(dot3_rn(r.wx, r.wy, r.wz, qx, qy, qz), ood);
+  vs = __fmul_rn(dot3_rn(wx, wy, wz, qx, qy, qz), ood);
   ds = __fmul_rn(dot3_rn(e1x, e1y, e1z, qx, qy, qz), ood);
   const bool xmask = (det > 0.00000001f) || (det < -0.00000001f);
   const bool umask = us >= 0.0f;
@@ -86,9 +106,65 @@ __device__ __forceinline__ uint32_t nibble_prefix(uint32_t counts, uint32_t slot
   return (pairs * 0x01010101u) >> 24;
 }
 
-__device__ __forceinline__ float qbyte(uint32_t w0, uint32_t w1, int i) {
-  const uint32_t w = i < 4 ? w0 : w1;
-  return (float)((w >> (8 * (i & 3))) & 0xffu);
+// byte i of the 8 quantised planes (w0 = slots 0-3, w1 = slots 4-7) as the float 1 + q * 2^-15:
+// one PRMT drops the byte into bits 8-15 under the exponent of 1.0 — no integer-to-float conversion
+// (I2F runs on the quarter-rate XU pipe; it was the top pipe of the first version of this kernel).
+__device__ __forceinline__ float qplane(uint32_t w0, uint32_t w1, int i) {
+  return __uint_as_float(__byte_perm(i < 4 ? w0 : w1, 0x3F800000u, 0x7604u + ((uint32_t)(i & 3) << 4)));
+}
+
+struct NodeHits {
+  uint32_t inner;       // hit inner children, key space (key = slot ^ oct)
+  uint32_t leaf;        // hit leaf children, key space
+  uint32_t imask;       // inner-child mask, slot space
+  uint32_t child_base;  // first inner child
+  uint32_t tri_base;    // first triangle of the node's leaves
+  uint32_t counts;      // 4-bit triangle count per slot
+};
+
+// Test a ray against the 8 quantised child boxes of one node.  dmax = cull distance.
+__device__ __forceinline__ NodeHits node_test(const DevAccel& A, uint32_t node, float ox, float oy, float oz, const RayDir& rd,
+                                              float dmax) {
+  const uint4* np = A.nodes + 5ull * node;
+  const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+  NodeHits h;
+  h.imask = n0.w >> 24;
+  h.child_base = n1.x;
+  h.tri_base = n1.y;
+  h.counts = n1.z;
+  // plane(q) = og + (2^15 + q) * 2^e  ->  t = fma(1 + q 2^-15, 2^(e+15) / dir, (og - org) / dir)
+  const float sx = __uint_as_float(((n0.w & 0xffu) + 15u) << 23) * rd.idx;
+  const float sy = __uint_as_float((((n0.w >> 8) & 0xffu) + 15u) << 23) * rd.idy;
+  const float sz = __uint_as_float((((n0.w >> 16) & 0xffu) + 15u) << 23) * rd.idz;
+  const float bx = (__uint_as_float(n0.x) - ox) * rd.idx;
+  const float by = (__uint_as_float(n0.y) - oy) * rd.idy;
+  const float bz = (__uint_as_float(n0.z) - oz) * rd.idz;
+  // near / far plane bytes by direction sign: lo = {n2.xy, n2.zw, n3.xy}, hi = {n3.zw, n4.xy, n4.zw}
+  const bool negx = rd.oct & 1u, negy = rd.oct & 2u, negz = rd.oct & 4u;
+  const uint32_t nx0 = negx ? n3.z : n2.x, nx1 = negx ? n3.w : n2.y;
+  const uint32_t fx0 = negx ? n2.x : n3.z, fx1 = negx ? n2.y : n3.w;
+  const uint32_t ny0 = negy ? n4.x : n2.z, ny1 = negy ? n4.y : n2.w;
+  const uint32_t fy0 = negy ? n2.z : n4.x, fy1 = negy ? n2.w : n4.y;
+  const uint32_t nz0 = negz ? n4.z : n3.x, nz1 = negz ? n4.w : n3.y;
+  const uint32_t fz0 = negz ? n3.x : n4.z, fz1 = negz ? n3.y : n4.w;
+  uint32_t hits = 0u;  // slot space
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float tnx = __fmaf_rn(qplane(nx0, nx1, i), sx, bx), tfx = __fmaf_rn(qplane(fx0, fx1, i), sx, bx);
+    const float tny = __fmaf_rn(qplane(ny0, ny1, i), sy, by), tfy = __fmaf_rn(qplane(fy0, fy1, i), sy, by);
+    const float tnz = __fmaf_rn(qplane(nz0, nz1, i), sz, bz), tfz = __fmaf_rn(qplane(fz0, fz1, i), sz, bz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, dmax));
+    hits |= (tn <= tf * PHOS_SLAB_SLACK ? 1u : 0u) << i;
+  }
+  // slot space -> key space: bit i moves to bit i ^ oct (three conditional swaps)
+  uint32_t both = (hits & h.imask) | ((hits & ~h.imask & 0xffu) << 8);
+  if (rd.oct & 1u) both = ((both & 0x5555u) << 1) | ((both >> 1) & 0x5555u);
+  if (rd.oct & 2u) both = ((both & 0x3333u) << 2) | ((both >> 2) & 0x3333u);
+  if (rd.oct & 4u) both = ((both & 0x0f0fu) << 4) | ((both >> 4) & 0x0f0fu);
+  h.inner = both & 0xffu;
+  h.leaf = both >> 8;
+  return h;
 }
 
 // Stack entry = a group of sibling inner nodes still to visit:
@@ -109,99 +185,73 @@ struct Stack {
   }
 };
 
-// Trace one ray; updates r in place.  Returns true when r changed (a hit was recorded).
+// take the nearest pending child out of a group: returns its node index
+__device__ __forceinline__ uint32_t take_child(uint2& group, uint32_t oct) {
+  const uint32_t key = __ffs(group.y >> 8) - 1;
+  group.y &= ~(0x100u << key);
+  const uint32_t slot = key ^ oct;
+  return group.x + __popc(group.y & ((1u << slot) - 1u) & 0xffu);
+}
+
+// closest-hit / any-hit acceptance of one Möller–Trumbore result; returns true when r changed
+__device__ __forceinline__ bool accept_hit(Ray& r, float ds, float us, float vs, const uint4 c) {
+  if (r.flags & PHOS_SHADOW) {
+    if (!(ds < r.d)) return false;
+    r.d = ds;
+    r.flags |= PHOS_HIT;
+    return true;
+  }
+  if (ds < r.d || (ds == r.d && (r.flags & PHOS_HIT) && c.w < r.order)) {
+    r.d = ds;
+    r.u = us;
+    r.v = vs;
+    r.mesh = c.y;
+    r.face = c.z;
+    r.order = c.w;
+    r.flags |= PHOS_HIT;
+    return true;
+  }
+  return false;
+}
+
+// Plain one-ray traversal (node, then its leaves, nearest octant first).  The production kernel
+// (trace.cuh) schedules the same node_test / mt_triangle / accept_hit steps warp-wide; this loop is
+// the straight-line statement of the algorithm, kept for the small-batch path and the host emulation
+// used by the CPU test-suite.  Returns true when r changed.
 template <bool kCount>
 __device__ __forceinline__ bool trace_ray(const DevAccel& A, Ray& r, Stack& st, uint32_t* n_nodes, uint32_t* n_tris) {
-  const bool shadow = (r.flags & PHOS_SHADOW) != 0;
-  // 1/dir, IEEE; a zero (or denormal-small) component is treated as +-2^-60 so no 0 * inf arises
-  const float tiny = 8.67361737988403547e-19f;  // 2^-60
-  const float dx = fabsf(r.wx) < tiny ? copysignf(tiny, r.wx) : r.wx;
-  const float dy = fabsf(r.wy) < tiny ? copysignf(tiny, r.wy) : r.wy;
-  const float dz = fabsf(r.wz) < tiny ? copysignf(tiny, r.wz) : r.wz;
-  const float idx = __fdiv_rn(1.0f, dx), idy = __fdiv_rn(1.0f, dy), idz = __fdiv_rn(1.0f, dz);
-  const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
-  const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
-
+  const RayDir rd = make_raydir(r.wx, r.wy, r.wz);
   bool changed = false;
   st.sp = 0;
-  uint2 cur = make_uint2(0u, 1u | ((1u << oct) << 8));  // the root as a one-node group in slot 0
-
+  uint2 cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
   for (;;) {
     if ((cur.y >> 8) == 0u) {
       if (st.sp == 0) break;
       cur = st.pop();
       continue;
     }
-    const uint32_t key = __ffs(cur.y >> 8) - 1;
-    cur.y &= ~(0x100u << key);
-    const uint32_t slot = key ^ oct;
-    const uint32_t node = cur.x + __popc(cur.y & ((1u << slot) - 1u) & 0xffu);
+    const uint32_t node = take_child(cur, rd.oct);
     if (cur.y >> 8) st.push(cur);
-
-    const uint4* np = A.nodes + 5ull * node;
-    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    NodeHits h = node_test(A, node, r.ox, r.oy, r.oz, rd, r.d * PHOS_CULL_SLACK);
     if (kCount) ++*n_nodes;
-    const uint32_t imask = n0.w >> 24;
-    const float sx = __uint_as_float((n0.w & 0xffu) << 23) * idx;
-    const float sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * idy;
-    const float sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * idz;
-    const float bx = (__uint_as_float(n0.x) - r.ox) * idx;
-    const float by = (__uint_as_float(n0.y) - r.oy) * idy;
-    const float bz = (__uint_as_float(n0.z) - r.oz) * idz;
-    // near / far plane bytes by direction sign: lo = {n2.xy, n2.zw, n3.xy}, hi = {n3.zw, n4.xy, n4.zw}
-    const uint32_t nx0 = negx ? n3.z : n2.x, nx1 = negx ? n3.w : n2.y;
-    const uint32_t fx0 = negx ? n2.x : n3.z, fx1 = negx ? n2.y : n3.w;
-    const uint32_t ny0 = negy ? n4.x : n2.z, ny1 = negy ? n4.y : n2.w;
-    const uint32_t fy0 = negy ? n2.z : n4.x, fy1 = negy ? n2.w : n4.y;
-    const uint32_t nz0 = negz ? n4.z : n3.x, nz1 = negz ? n4.w : n3.y;
-    const uint32_t fz0 = negz ? n3.x : n4.z, fz1 = negz ? n3.y : n4.w;
-    const float dmax = r.d * PHOS_CULL_SLACK;
-    uint32_t hit_inner = 0u, hit_leaf = 0u;  // key space
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float tnx = __fmaf_rn(qbyte(nx0, nx1, i), sx, bx), tfx = __fmaf_rn(qbyte(fx0, fx1, i), sx, bx);
-      const float tny = __fmaf_rn(qbyte(ny0, ny1, i), sy, by), tfy = __fmaf_rn(qbyte(fy0, fy1, i), sy, by);
-      const float tnz = __fmaf_rn(qbyte(nz0, nz1, i), sz, bz), tfz = __fmaf_rn(qbyte(fz0, fz1, i), sz, bz);
-      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, dmax));
-      const uint32_t h = tn <= tf * PHOS_SLAB_SLACK ? 1u : 0u;
-      const uint32_t inner = (imask >> i) & 1u;
-      hit_inner |= (h & inner) << (i ^ oct);
-      hit_leaf |= (h & (inner ^ 1u)) << (i ^ oct);
-    }
-
     // leaves first (they shrink d before any child node is opened), nearest octant first
-    const uint32_t counts = n1.z;
-    while (hit_leaf) {
-      const uint32_t lkey = __ffs(hit_leaf) - 1;
-      hit_leaf &= hit_leaf - 1;
-      const uint32_t lslot = lkey ^ oct;
-      const uint32_t cnt = (counts >> (4 * lslot)) & 15u;  // 0 for an empty slot
-      const uint4* tp = A.tris + 3ull * (n1.y + nibble_prefix(counts, lslot));
+    while (h.leaf) {
+      const uint32_t lslot = (__ffs(h.leaf) - 1) ^ rd.oct;
+      h.leaf &= h.leaf - 1;
+      const uint32_t cnt = (h.counts >> (4 * lslot)) & 15u;  // 0 for an empty slot
+      const uint4* tp = A.tris + 3ull * (h.tri_base + nibble_prefix(h.counts, lslot));
       for (uint32_t k = 0; k < cnt; ++k, tp += 3) {
         const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         if (kCount) ++*n_tris;
         float ds, us, vs;
-        if (!mt_triangle(a, b, c, r, ds, us, vs)) continue;
-        if (shadow) {
-          if (ds < r.d) {
-            r.d = ds;
-            r.flags |= PHOS_HIT;
-            return true;
-          }
-        } else if (ds < r.d || (ds == r.d && (r.flags & PHOS_HIT) && c.w < r.order)) {
-          r.d = ds;
-          r.u = us;
-          r.v = vs;
-          r.mesh = c.y;
-          r.face = c.z;
-          r.order = c.w;
-          r.flags |= PHOS_HIT;
+        if (!mt_triangle(a, b, c, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs)) continue;
+        if (accept_hit(r, ds, us, vs, c)) {
           changed = true;
+          if (r.flags & PHOS_SHADOW) return true;
         }
       }
     }
-    cur = make_uint2(n1.x, imask | (hit_inner << 8));
+    cur = make_uint2(h.child_base, h.imask | (h.inner << 8));
   }
   return changed;
 }

@@ -21,6 +21,12 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline uint4 __ldg(const uint4* p) { return *p; }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+  const uint64_t t = ((uint64_t)y << 32) | x;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= (uint32_t)((t >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+  return r;
+}
 
 #include "../../phosphorus_mk2_b200/csrc/phos_internal.hpp"
 #include "../../phosphorus_mk2_b200/csrc/trace_ray.cuh"
