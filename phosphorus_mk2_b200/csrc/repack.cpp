@@ -2,21 +2,33 @@
 //
 // Input is mbvh_t::root / mbvh_t::triangles exactly as the reference builder publishes them
 // (reference src/accel/bvh.cpp:42-47; node semantics src/accel/bvh/node.hpp:25-67; leaf = packets
-// offset .. offset + ceil(num/8) - 1, src/kernels/cpu/stream_bvh_kernel.cpp:126-142).  The topology
-// and the triangle set are kept; only the storage changes:
-//   * nodes are renumbered breadth-first so a node's inner children are contiguous (popcount
-//     addressing) and its leaf children's triangles are contiguous;
-//   * child boxes are quantised outwards to 8 bits per plane — any ray that meets the real box
-//     meets the quantised one, so the set of triangles a ray can reach never shrinks;
-//   * the half-empty 8-wide SoA packets (4.2 of 8 lanes used on average) become 48 B triangles;
-//   * children are placed in slots so that slot ^ octant approximates front-to-back order;
-//   * a leaf of more than 15 triangles (the reference's uint8 count allows up to 255 and silently
-//     wraps beyond, node.hpp:19) is turned into a small sub-tree of <= 15-triangle leaves.
+// offset .. offset + ceil(num/8) - 1, src/kernels/cpu/stream_bvh_kernel.cpp:126-142).
+//
+// What is kept: every triangle, bit for bit (e0, e1, v0 as the reference packet holds them, ids, and
+// its packet * 8 + lane position, the brute-force visiting order that breaks exact-t ties), and the
+// reference's leaves — the set of triangles the SAH build decided to keep together.
+// What changes, because the result of a ray query does not depend on it:
+//   * the inner topology is re-grouped.  The reference widens a node by re-splitting its SMALLEST
+//     child (binned_sah_builder.hpp:198-213), which yields long chains of "7 small children + 1
+//     huge child" (depth 20 at 10 M triangles, 5.4 of 8 slots used).  Here the reference leaves are
+//     re-grouped top-down with a binned SAH over leaf boxes, always splitting the LARGEST range
+//     until a node has 8 children: a balanced 8-wide tree over the same leaves (depth ~8);
+//   * child boxes are quantised outwards to 8 bits per plane on a per-node power-of-two grid — any
+//     ray that meets the real box meets the quantised one;
+//   * the half-empty 8-wide SoA packets (4.2 of 8 lanes used) become 48 B triangles, stored so that
+//     a node's leaf triangles are contiguous; nodes are numbered breadth-first so a node's inner
+//     children are contiguous (popcount addressing);
+//   * children are placed in slots so that slot ^ ray-octant approximates front-to-back order;
+//   * small sibling leaves may be fused (<= PHOS_REPACK_MERGE triangles) and a leaf of more than 15
+//     triangles (the reference's uint8 count allows 255 and wraps beyond, node.hpp:19) is cut into
+//     <= 15-triangle leaves.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <numeric>
 
 #include "phos_internal.hpp"
 
@@ -39,7 +51,10 @@ struct DBox {
       hi[a] = std::max(hi[a], p[a]);
     }
   }
-  bool empty() const { return lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]; }
+  double half_area() const {
+    const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx < 0 ? 0.0 : dx * dy + dx * dz + dy * dz;
+  }
 };
 
 // Box of a triangle as Möller–Trumbore sees it (v0, v0 + e0, v0 + e1), padded by one fp32 ulp of the
@@ -57,52 +72,113 @@ DBox tri_box(const GTri& t) {
   return b;
 }
 
-struct Child {
-  DBox box;
-  int32_t ref_node = -1;    // inner child coming from the reference tree
-  std::vector<GTri> tris;   // leaf child, or synthetic inner child when > 15 triangles
-  bool synthetic_inner = false;
-};
-
-struct Work {
-  int32_t ref_node = -1;
-  std::vector<GTri> tris;  // synthetic node: split these
-  uint32_t depth = 0;
-};
-
 constexpr uint32_t kMaxLeaf = 15;
+constexpr int kBins = 16;
 
-// split an oversized triangle list into <= 8 spatially sorted groups
-void split_synthetic(std::vector<GTri>& tris, std::vector<Child>& out) {
-  DBox cb;
-  std::vector<std::pair<double, uint32_t>> key(tris.size());
-  for (const GTri& t : tris) cb.grow(tri_box(t));
-  int axis = 0;
-  for (int a = 1; a < 3; ++a)
-    if (cb.hi[a] - cb.lo[a] > cb.hi[axis] - cb.lo[axis]) axis = a;
-  for (uint32_t i = 0; i < tris.size(); ++i) {
-    const DBox b = tri_box(tris[i]);
-    key[i] = {b.lo[axis] + b.hi[axis], i};
-  }
-  std::sort(key.begin(), key.end());
-  const size_t groups = std::min<size_t>(8, (tris.size() + kMaxLeaf - 1) / kMaxLeaf);
-  for (size_t g = 0; g < groups; ++g) {
-    const size_t b = tris.size() * g / groups, e = tris.size() * (g + 1) / groups;
-    Child c;
-    for (size_t i = b; i < e; ++i) {
-      c.tris.push_back(tris[key[i].second]);
-      c.box.grow(tri_box(c.tris.back()));
+// one reference leaf (or a <= 15-triangle piece of an oversized one): the unit that is re-grouped
+struct Prim {
+  DBox box;
+  double c[3];         // box centre
+  uint32_t tri_begin;  // into the extracted triangle array
+  uint32_t tri_count;
+};
+
+struct Range {
+  uint32_t begin, end;  // into the prim index array
+  DBox box;
+  uint32_t tris;
+  uint32_t count() const { return end - begin; }
+};
+
+struct Builder {
+  const std::vector<Prim>& prims;
+  std::vector<uint32_t>& idx;
+
+  Range make_range(uint32_t b, uint32_t e) const {
+    Range r;
+    r.begin = b;
+    r.end = e;
+    r.tris = 0;
+    for (uint32_t i = b; i < e; ++i) {
+      r.box.grow(prims[idx[i]].box);
+      r.tris += prims[idx[i]].tri_count;
     }
-    c.synthetic_inner = c.tris.size() > kMaxLeaf;
-    out.push_back(std::move(c));
+    return r;
   }
-}
+
+  // binned SAH split of a range of leaves (cost weighted by triangle count); median split when the
+  // centroids do not separate.  Always produces two non-empty halves for count >= 2.
+  void split(const Range& r, Range& l, Range& rr) {
+    DBox cb;
+    for (uint32_t i = r.begin; i < r.end; ++i) cb.grow(prims[idx[i]].c[0], prims[idx[i]].c[1], prims[idx[i]].c[2]);
+    int best_axis = -1, best_bin = 0;
+    double best_cost = DBL_MAX;
+    for (int a = 0; a < 3; ++a) {
+      const double ext = cb.hi[a] - cb.lo[a];
+      if (!(ext > 0.0)) continue;
+      DBox bb[kBins];
+      uint32_t bn[kBins] = {0};
+      const double k = kBins / ext;
+      for (uint32_t i = r.begin; i < r.end; ++i) {
+        const Prim& p = prims[idx[i]];
+        const int b = std::min(kBins - 1, (int)((p.c[a] - cb.lo[a]) * k));
+        bb[b].grow(p.box);
+        bn[b] += p.tri_count;
+      }
+      DBox suf[kBins];
+      uint32_t sufn[kBins];
+      DBox acc;
+      uint32_t n = 0;
+      for (int j = kBins - 1; j >= 0; --j) {
+        acc.grow(bb[j]);
+        n += bn[j];
+        suf[j] = acc;
+        sufn[j] = n;
+      }
+      DBox left;
+      uint32_t nl = 0;
+      for (int j = 0; j < kBins - 1; ++j) {
+        left.grow(bb[j]);
+        nl += bn[j];
+        if (nl == 0 || sufn[j + 1] == 0) continue;
+        const double cost = left.half_area() * nl + suf[j + 1].half_area() * sufn[j + 1];
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_axis = a;
+          best_bin = j;
+        }
+      }
+    }
+    uint32_t mid = r.begin;
+    if (best_axis >= 0) {
+      const double k = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+      const double lo = cb.lo[best_axis];
+      const int a = best_axis, bin = best_bin;
+      uint32_t* m = std::partition(idx.data() + r.begin, idx.data() + r.end, [&](uint32_t i) {
+        return std::min(kBins - 1, (int)((prims[i].c[a] - lo) * k)) <= bin;
+      });
+      mid = (uint32_t)(m - idx.data());
+    }
+    if (mid == r.begin || mid == r.end) {  // degenerate: split by count along the widest centroid axis
+      int a = 0;
+      for (int k = 1; k < 3; ++k)
+        if (cb.hi[k] - cb.lo[k] > cb.hi[a] - cb.lo[a]) a = k;
+      mid = r.begin + r.count() / 2;
+      std::nth_element(idx.begin() + r.begin, idx.begin() + mid, idx.begin() + r.end,
+                       [&](uint32_t x, uint32_t y) { return prims[x].c[a] < prims[y].c[a]; });
+    }
+    l = make_range(r.begin, mid);
+    rr = make_range(mid, r.end);
+  }
+};
 
 }  // namespace
 
 bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packets, uint32_t n_packets, PackedAccel& out,
                   std::string& err) {
   out = PackedAccel();
+  uint32_t merge_limit = 0;  // fuse sibling leaves up to this many triangles (0: keep the reference leaves)
+  if (const char* e = std::getenv("PHOS_REPACK_MERGE")) merge_limit = std::min<uint32_t>(kMaxLeaf, (uint32_t)std::atoi(e));
   if (!nodes || !packets || n_nodes == 0 || n_packets == 0) {
     err = "empty acceleration structure (the reference builder emits no node for < 8 triangles)";
     return false;
@@ -110,10 +186,13 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
 
   // Real packet count of every leaf: ceil(num/8), unless the gap to the next leaf's first packet
   // shows the uint8 count wrapped (true count = num + 256 k).
+  auto slot_live = [&](const RefNode& rn, int i) {
+    return !(rn.bounds[i] > rn.bounds[i + 24] || rn.bounds[i + 8] > rn.bounds[i + 32] || rn.bounds[i + 16] > rn.bounds[i + 40]);
+  };
   std::vector<uint32_t> leaf_offsets;
   for (uint32_t n = 0; n < n_nodes; ++n)
     for (int i = 0; i < 8; ++i)
-      if (nodes[n].flags[i] == 1 && !(nodes[n].bounds[i] > nodes[n].bounds[i + 24])) leaf_offsets.push_back(nodes[n].offset[i]);
+      if (nodes[n].flags[i] == 1 && slot_live(nodes[n], i)) leaf_offsets.push_back(nodes[n].offset[i]);
   std::sort(leaf_offsets.begin(), leaf_offsets.end());
   auto leaf_packets = [&](uint32_t offset, uint32_t num) -> uint32_t {
     uint32_t npk = (num + 7) / 8;
@@ -130,106 +209,168 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
     return npk;
   };
 
-  std::vector<uint8_t> visited(n_nodes, 0);
+  // ---- A. walk the reference tree: validate it, pull out every leaf's triangles --------------------
+  std::vector<GTri> tris;
+  std::vector<Prim> prims;
+  tris.reserve((size_t)n_packets * 5);
+  {
+    std::vector<uint8_t> visited(n_nodes, 0);
+    std::vector<uint32_t> stack{0};
+    while (!stack.empty()) {
+      const uint32_t n = stack.back();
+      stack.pop_back();
+      if (n >= n_nodes || visited[n]) {
+        err = "node graph is not a tree (bad or repeated child index)";
+        return false;
+      }
+      visited[n] = 1;
+      const RefNode& rn = nodes[n];
+      bool any = false;
+      for (int i = 7; i >= 0; --i) {
+        if (!slot_live(rn, i)) continue;
+        any = true;
+        for (int a = 0; a < 6; ++a)
+          if (!std::isfinite(rn.bounds[i + 8 * a])) {
+            err = "non-finite child bounds";
+            return false;
+          }
+        if (rn.flags[i] != 1) {
+          stack.push_back(rn.offset[i]);
+          continue;
+        }
+        const uint32_t npk = leaf_packets(rn.offset[i], rn.num[i]);
+        if ((uint64_t)rn.offset[i] + npk > n_packets) {
+          err = "leaf packet range out of bounds";
+          return false;
+        }
+        const uint32_t first = (uint32_t)tris.size();
+        for (uint32_t p = rn.offset[i]; p < rn.offset[i] + npk; ++p) {
+          const RefPacket& pk = packets[p];
+          if (pk.num > 8) {
+            err = "packet with more than 8 triangles";
+            return false;
+          }
+          for (uint32_t j = 0; j < pk.num; ++j) {
+            GTri t;
+            t.v0x = pk.v0x[j]; t.v0y = pk.v0y[j]; t.v0z = pk.v0z[j];
+            t.e0x = pk.e0x[j]; t.e0y = pk.e0y[j]; t.e0z = pk.e0z[j];
+            t.e1x = pk.e1x[j]; t.e1y = pk.e1y[j]; t.e1z = pk.e1z[j];
+            t.meshid = pk.meshid[j];
+            t.faceid = pk.faceid[j];
+            t.order = p * 8 + j;
+            tris.push_back(t);
+          }
+        }
+        // one prim per <= 15 triangles (an oversized leaf is cut along its longest axis)
+        uint32_t cnt = (uint32_t)tris.size() - first;
+        if (cnt > kMaxLeaf) {
+          DBox cb;
+          for (uint32_t k = first; k < first + cnt; ++k) cb.grow(tri_box(tris[k]));
+          int ax = 0;
+          for (int a = 1; a < 3; ++a)
+            if (cb.hi[a] - cb.lo[a] > cb.hi[ax] - cb.lo[ax]) ax = a;
+          std::sort(tris.begin() + first, tris.end(), [&](const GTri& x, const GTri& y) {
+            const DBox bx = tri_box(x), by = tri_box(y);
+            return bx.lo[ax] + bx.hi[ax] < by.lo[ax] + by.hi[ax];
+          });
+        }
+        for (uint32_t b = 0; b < cnt;) {
+          const uint32_t pieces = (cnt - b + kMaxLeaf - 1) / kMaxLeaf;
+          const uint32_t take = (cnt - b + pieces - 1) / pieces;
+          Prim p;
+          p.tri_begin = first + b;
+          p.tri_count = take;
+          for (uint32_t k = 0; k < take; ++k) p.box.grow(tri_box(tris[first + b + k]));
+          for (int a = 0; a < 3; ++a) p.c[a] = 0.5 * (p.box.lo[a] + p.box.hi[a]);
+          prims.push_back(p);
+          b += take;
+        }
+      }
+      if (!any) {
+        err = "inner node without children";
+        return false;
+      }
+    }
+  }
+  if (tris.empty() || prims.empty()) {
+    err = "acceleration structure holds no triangles";
+    return false;
+  }
+
+  // ---- B. re-group the leaves into a balanced 8-wide tree, breadth first ------------------------------
+  std::vector<uint32_t> idx(prims.size());
+  std::iota(idx.begin(), idx.end(), 0u);
+  Builder B{prims, idx};
+  struct Work {
+    Range range;
+    uint32_t depth;
+  };
   std::deque<Work> queue;
-  Work root;
-  root.ref_node = 0;
-  queue.push_back(std::move(root));
-  out.nodes.reserve(n_nodes + 16);
-  out.tris.reserve((size_t)n_packets * 5);
+  queue.push_back({B.make_range(0, (uint32_t)prims.size()), 0});
+  out.nodes.reserve(prims.size() / 4 + 16);
+  out.tris.reserve(tris.size());
+
+  auto is_leaf = [&](const Range& r) { return r.count() == 1 || r.tris <= merge_limit; };
 
   while (!queue.empty()) {
-    Work w = std::move(queue.front());
+    const Work w = queue.front();
     queue.pop_front();
     const uint32_t self = (uint32_t)out.nodes.size();
     out.nodes.emplace_back();
     out.max_depth = std::max(out.max_depth, w.depth);
 
-    // ---- gather children ---------------------------------------------------------------------
-    std::vector<Child> children;
-    if (w.ref_node >= 0) {
-      if ((uint32_t)w.ref_node >= n_nodes || visited[w.ref_node]) {
-        err = "node graph is not a tree (bad or repeated child index)";
-        return false;
-      }
-      visited[w.ref_node] = 1;
-      const RefNode& rn = nodes[w.ref_node];
-      for (int i = 0; i < 8; ++i) {
-        if (rn.bounds[i] > rn.bounds[i + 24] || rn.bounds[i + 8] > rn.bounds[i + 32] || rn.bounds[i + 16] > rn.bounds[i + 40])
-          continue;  // empty slot: min = +FLT_MAX, max = -FLT_MAX
-        Child c;
-        c.box.lo[0] = rn.bounds[i];      c.box.lo[1] = rn.bounds[i + 8];  c.box.lo[2] = rn.bounds[i + 16];
-        c.box.hi[0] = rn.bounds[i + 24]; c.box.hi[1] = rn.bounds[i + 32]; c.box.hi[2] = rn.bounds[i + 40];
-        for (int a = 0; a < 3; ++a)
-          if (!std::isfinite(c.box.lo[a]) || !std::isfinite(c.box.hi[a])) {
-            err = "non-finite child bounds";
-            return false;
-          }
-        if (rn.flags[i] == 1) {
-          const uint32_t npk = leaf_packets(rn.offset[i], rn.num[i]);
-          if (npk == 0) continue;
-          if ((uint64_t)rn.offset[i] + npk > n_packets) {
-            err = "leaf packet range out of bounds";
-            return false;
-          }
-          for (uint32_t p = rn.offset[i]; p < rn.offset[i] + npk; ++p) {
-            const RefPacket& pk = packets[p];
-            if (pk.num > 8) {
-              err = "packet with more than 8 triangles";
-              return false;
-            }
-            for (uint32_t j = 0; j < pk.num; ++j) {
-              GTri t;
-              t.v0x = pk.v0x[j]; t.v0y = pk.v0y[j]; t.v0z = pk.v0z[j];
-              t.e0x = pk.e0x[j]; t.e0y = pk.e0y[j]; t.e0z = pk.e0z[j];
-              t.e1x = pk.e1x[j]; t.e1y = pk.e1y[j]; t.e1z = pk.e1z[j];
-              t.meshid = pk.meshid[j];
-              t.faceid = pk.faceid[j];
-              t.order = p * 8 + j;
-              c.tris.push_back(t);
-            }
-          }
-          if (c.tris.empty()) continue;
-          c.synthetic_inner = c.tris.size() > kMaxLeaf;
-        } else {
-          c.ref_node = (int32_t)rn.offset[i];
-        }
-        children.push_back(std::move(c));
-      }
+    // children: split the largest splittable range until there are 8
+    Range child[8];
+    int nc = 1;
+    child[0] = w.range;
+    if (w.range.count() == 1) {
+      // a single leaf under a node of its own only happens for a one-leaf tree
     } else {
-      split_synthetic(w.tris, children);
-    }
-    if (children.empty()) {
-      err = "inner node without children";
-      return false;
+      while (nc < 8) {
+        int pick = -1;
+        double best = -1.0;
+        for (int i = 0; i < nc; ++i) {
+          if (is_leaf(child[i]) && !(nc == 1)) continue;
+          if (child[i].count() < 2) continue;
+          const double a = child[i].box.half_area();
+          if (a > best) {
+            best = a;
+            pick = i;
+          }
+        }
+        if (pick < 0) break;
+        Range l, r;
+        B.split(child[pick], l, r);
+        child[pick] = l;
+        child[nc++] = r;
+      }
     }
 
     // ---- slot assignment: greedy max of dot(child centre - node centre, slot sign vector) -------
     DBox nb;
-    for (const Child& c : children) nb.grow(c.box);
+    for (int i = 0; i < nc; ++i) nb.grow(child[i].box);
     int slot_of[8];
     {
-      const size_t nc = children.size();
       double score[8][8];
-      for (size_t i = 0; i < nc; ++i)
+      for (int i = 0; i < nc; ++i)
         for (int s = 0; s < 8; ++s) {
           double v = 0.0;
           for (int a = 0; a < 3; ++a) {
-            const double rel = 0.5 * (children[i].box.lo[a] + children[i].box.hi[a]) - 0.5 * (nb.lo[a] + nb.hi[a]);
+            const double rel = 0.5 * (child[i].box.lo[a] + child[i].box.hi[a]) - 0.5 * (nb.lo[a] + nb.hi[a]);
             v += ((s >> a) & 1) ? rel : -rel;
           }
           score[i][s] = v;
         }
       bool child_done[8] = {false}, slot_used[8] = {false};
-      for (size_t round = 0; round < nc; ++round) {
+      for (int round = 0; round < nc; ++round) {
         double best = -DBL_MAX;
         int bi = -1, bs = -1;
-        for (size_t i = 0; i < nc; ++i) {
+        for (int i = 0; i < nc; ++i) {
           if (child_done[i]) continue;
           for (int s = 0; s < 8; ++s)
             if (!slot_used[s] && score[i][s] > best) {
               best = score[i][s];
-              bi = (int)i;
+              bi = i;
               bs = s;
             }
         }
@@ -240,7 +381,7 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
     }
     int child_in_slot[8];
     for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
-    for (size_t i = 0; i < children.size(); ++i) child_in_slot[slot_of[i]] = (int)i;
+    for (int i = 0; i < nc; ++i) child_in_slot[slot_of[i]] = i;
 
     // ---- quantisation grid -----------------------------------------------------------------------
     GNode g;
@@ -291,10 +432,10 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
     for (int s = 0; s < 8; ++s) {
       const int ci = child_in_slot[s];
       if (ci < 0) continue;
-      Child& c = children[ci];
+      const Range& c = child[ci];
       for (int a = 0; a < 3; ++a) {
-        double ql = std::floor((c.box.lo[a] - o[a]) / scale[a] - margin);
-        double qh = std::ceil((c.box.hi[a] - o[a]) / scale[a] + margin);
+        const double ql = std::floor((c.box.lo[a] - o[a]) / scale[a] - margin);
+        const double qh = std::ceil((c.box.hi[a] - o[a]) / scale[a] + margin);
         if (ql < 0.0 || qh > 255.0 || o[a] + (ql + margin) * scale[a] > c.box.lo[a] ||
             o[a] + (qh - margin) * scale[a] < c.box.hi[a]) {
           err = "internal: quantised box does not contain the child box";
@@ -303,23 +444,22 @@ bool repack_accel(const RefNode* nodes, uint32_t n_nodes, const RefPacket* packe
         qlo[a][s] = (uint8_t)ql;
         qhi[a][s] = (uint8_t)qh;
       }
-      if (c.ref_node >= 0 || c.synthetic_inner) {
-        g.imask |= (uint8_t)(1u << s);
-        Work cw;
-        cw.ref_node = c.ref_node;
-        cw.depth = w.depth + 1;
-        if (c.synthetic_inner) cw.tris = std::move(c.tris);
-        queue.push_back(std::move(cw));
+      if ((c.count() == 1 || (nc > 1 && is_leaf(c))) && c.tris <= kMaxLeaf) {
+        g.counts |= c.tris << (4 * s);
+        out.max_leaf_tris = std::max(out.max_leaf_tris, c.tris);
+        for (uint32_t i = c.begin; i < c.end; ++i) {
+          const Prim& p = prims[idx[i]];
+          out.tris.insert(out.tris.end(), tris.begin() + p.tri_begin, tris.begin() + p.tri_begin + p.tri_count);
+        }
       } else {
-        g.counts |= (uint32_t)c.tris.size() << (4 * s);
-        out.max_leaf_tris = std::max<uint32_t>(out.max_leaf_tris, (uint32_t)c.tris.size());
-        for (const GTri& t : c.tris) out.tris.push_back(t);
+        g.imask |= (uint8_t)(1u << s);
+        queue.push_back({c, w.depth + 1});
       }
     }
     out.nodes[self] = g;
   }
-  if (out.tris.empty()) {
-    err = "acceleration structure holds no triangles";
+  if (out.tris.size() != tris.size()) {
+    err = "internal: triangle count changed during re-pack";
     return false;
   }
   return true;

@@ -19,8 +19,24 @@
 
 namespace phos {
 
-constexpr int kChunk = 64;      // rays per claimed chunk
-constexpr int kRefillMin = 6;   // idle lanes that trigger a refill
+// tuning knobs (defaults chosen by tools/sweep.py runs on the B200, see profiles/)
+#ifndef PHOS_CHUNK
+#define PHOS_CHUNK 64
+#endif
+#ifndef PHOS_REFILL_MIN
+#define PHOS_REFILL_MIN 6
+#endif
+#ifndef PHOS_TRI_BIAS
+#define PHOS_TRI_BIAS 2
+#endif
+#ifndef PHOS_MIN_BLOCKS
+#define PHOS_MIN_BLOCKS 6
+#endif
+#ifndef PHOS_PREFETCH
+#define PHOS_PREFETCH 0
+#endif
+constexpr int kChunk = PHOS_CHUNK;           // rays per claimed chunk
+constexpr int kRefillMin = PHOS_REFILL_MIN;  // idle lanes that trigger a refill
 constexpr int kTraceWarps = kTraceBlock / 32;
 
 struct TraceArgs {
@@ -57,7 +73,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 }
 
 template <bool kCount>
-__global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs P) {
+__global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(const TraceArgs P) {
   __shared__ uint2 s_stack[kSmemStack * kTraceBlock];
   __shared__ alignas(128) uint32_t s_stage[kTraceWarps][2][8][kChunk];
   __shared__ alignas(8) unsigned long long s_bar[kTraceWarps][2];
@@ -198,7 +214,8 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs P) {
     if (act == 0u) break;  // stream drained and every lane retired
     const bool tri_work = has_ray && (trem | lmask) != 0u;
     const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
-    if (__popc(tl) >= __popc(act & ~tl)) {
+    // a triangle step is cheaper than a node step: PHOS_TRI_BIAS weights the vote
+    if (PHOS_TRI_BIAS * __popc(tl) >= __popc(act & ~tl)) {
       if (tri_work) {
         if (trem == 0u) {  // open the next hit leaf, nearest octant first
           const uint32_t slot = (__ffs(lmask) - 1) ^ rd.oct;
@@ -234,6 +251,19 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs P) {
         lcounts = h.counts;
         lbase = h.tri_base;
         cur = make_uint2(h.child_base, h.imask | (h.inner << 8));
+#if PHOS_PREFETCH
+        if (h.inner) {  // the child this ray opens next: pull its 80 bytes towards L1 while other work runs
+          uint2 peek = cur;
+          const char* nn = (const char*)(P.accel.nodes + 5ull * take_child(peek, rd.oct));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(nn));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(nn + 64));
+        }
+        if (h.leaf) {
+          const uint32_t slot = (__ffs(h.leaf) - 1) ^ rd.oct;
+          const char* tt = (const char*)(P.accel.tris + 3ull * (h.tri_base + nibble_prefix(h.counts, slot)));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(tt));
+        }
+#endif
       }
     }
   }

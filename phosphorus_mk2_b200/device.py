@@ -120,8 +120,8 @@ class DeviceRays:
 class CudaDevice:
     """cuda_t : xpu_t — one B200."""
 
-    def __init__(self, options: Options, device: int = 0):
-        self._L = _lib.load()
+    def __init__(self, options: Options, device: int = 0, lib_path: str | None = None):
+        self._L = _lib.load(lib_path)
         self.options = options
         self.device = device
         o = PhosOptions(options.samples_per_pixel, options.paths_per_sample, options.path_depth)

@@ -75,21 +75,22 @@ SYMBOLS = {
     "phos_cuda_camera_rays": (_I, [_VP, C.POINTER(PhosTile), _U32, C.c_float, C.c_float, _RP]),
 }
 
-_lib = None
+_libs: dict = {}
 
 
-def load() -> C.CDLL:
-    """Load libphos_cuda.so and bind every declared symbol; raises PhosError if it is not built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise PhosError(f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+def load(path: str | None = None) -> C.CDLL:
+    """Load libphos_cuda.so (or a tuning variant given by `path` / $PHOS_CUDA_LIB) and bind every
+    declared symbol; raises PhosError if it is not built."""
+    path = path or os.environ.get("PHOS_CUDA_LIB") or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise PhosError(f"{path} is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "or `make -C phosphorus_mk2_b200/csrc`); there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    _libs[path] = lib
     return lib
