@@ -151,6 +151,23 @@ int phos_cuda_upload_scene(phos_ctx* ctx, const phos_scene_desc* scene);
 int phos_cuda_camera_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, float jx, float jy,
                           const phos_rays* device_rays);
 
+/* tile_renderer_t::render_tile over a list of tiles (src/xpu/cpu.cpp:156-205), as a wavefront: path-trace
+ * samples [spp_begin, spp_end) of every pixel of the given tiles and accumulate
+ * radiance / (spp_total * paths_per_sample) into the ctx's device film (film size = camera film size).
+ * Depth and paths_per_sample come from the phos_options the ctx was created with.  Random numbers
+ * are a pure function of (seed, film pixel, sample, bounce, dimension): the image does not depend on
+ * how tiles or sample ranges are split over calls or GPUs.  Asynchronous on the ctx stream. */
+int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, uint32_t spp_begin, uint32_t spp_end,
+                     uint32_t spp_total, uint64_t seed);
+
+/* ---- film: the film_t<>::add_tile hand-off (src/film.hpp:10-16) -------------------------------------- */
+int phos_cuda_film_clear(phos_ctx* ctx);
+/* device pointer of the W*H*4 float film (for the per-frame NCCL reduce done by the caller) */
+int phos_cuda_film_device_ptr(phos_ctx* ctx, void** out_ptr, uint64_t* out_floats);
+/* copy a rectangle of the film to host as interleaved RGBA (alpha = 1 where rendered): the tile
+ * buffer film_t<>::add_tile receives.  Blocking. */
+int phos_cuda_film_read(phos_ctx* ctx, float* rgba, uint32_t x, uint32_t y, uint32_t w, uint32_t h);
+
 #ifdef __cplusplus
 }
 #endif

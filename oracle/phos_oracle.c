@@ -21,6 +21,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 /* flag bits, src/state.hpp:33-36 */
 #define ORC_HIT 1u
@@ -168,8 +171,12 @@ typedef struct {
  * instead of the reference's per-stream summed-distance order (:99-115).  Neither changes the
  * result: the closest accepted triangle, ties broken like the brute-force kernel (lowest packet,
  * then lowest lane).  Validated == orc_brute_force in tests/test_oracle_pin.py.
- * mode_ties: 1 = break exact-t ties by lowest (packet, lane) like brute force (default),
- *            0 = first-found strict '<' (the stream kernel's own rule). */
+ * mode_ties: bit 0: 1 = break exact-t ties by lowest (packet, lane) like brute force (default),
+ *                   0 = first-found strict '<' (the stream kernel's own rule);
+ *            bit 1: 1 = REFERENCE-EMULATION slab test (x86 only): 1/dir from the RCPSS instruction and
+ *                   fp32 planes exactly as aabb.hpp:33-61 / stream_bvh_kernel.cpp:66-72, no widening —
+ *                   reproduces the reference stream kernel's false misses; used only to show that
+ *                   the oracle models the reference renderer (tests/test_oracle_render.py). */
 void orc_traverse(const orc_node* nodes, const orc_packet* packets, orc_rays* rays, uint64_t n, orc_counters* c,
                   int mode_ties) {
   orc_ref stack[512];
@@ -181,6 +188,15 @@ void orc_traverse(const orc_node* nodes, const orc_packet* packets, orc_rays* ra
     const double ox = rays->px[i], oy = rays->py[i], oz = rays->pz[i];
     const double idx = 1.0 / (double)rays->wx[i], idy = 1.0 / (double)rays->wy[i], idz = 1.0 / (double)rays->wz[i];
     const int shadow = (rays->flags[i] & ORC_SHADOW) != 0;
+    const int emulate = (mode_ties & 2) != 0;
+    float ridx = 0, ridy = 0, ridz = 0;
+#if defined(__x86_64__)
+    if (emulate) {
+      ridx = _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(rays->wx[i])));
+      ridy = _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(rays->wy[i])));
+      ridz = _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(rays->wz[i])));
+    }
+#endif
     /* best (packet, lane) for tie-breaking */
     uint32_t best_packet = 0xffffffffu;
     int top = 0;
@@ -192,7 +208,7 @@ void orc_traverse(const orc_node* nodes, const orc_packet* packets, orc_rays* ra
       if ((uint64_t)top > cnt.max_stack) cnt.max_stack = (uint64_t)top;
       const orc_ref cur = stack[--top];
       const double d = rays->d[i];
-      if ((double)cur.dist > d * (1.0 + 1e-6) + 1e-30) continue;
+      if (!emulate && (double)cur.dist > d * (1.0 + 1e-6) + 1e-30) continue;
       if (cur.prims == 0xffffffffu) {
         if (shadow && (rays->flags[i] & ORC_HIT)) continue;
         const orc_node* nd = &nodes[cur.offset];
@@ -203,6 +219,24 @@ void orc_traverse(const orc_node* nodes, const orc_packet* packets, orc_rays* ra
           const double bx0 = nd->bounds[k], by0 = nd->bounds[k + 8], bz0 = nd->bounds[k + 16];
           const double bx1 = nd->bounds[k + 24], by1 = nd->bounds[k + 32], bz1 = nd->bounds[k + 40];
           if (bx0 > bx1) continue; /* empty child: min=+FLT_MAX, max=-FLT_MAX (node.hpp:25-29) */
+          if (emulate) {
+            const float o_x = rays->px[i], o_y = rays->py[i], o_z = rays->pz[i], dcur = rays->d[i];
+            const float mnx = ((ridx >= 0.0f ? nd->bounds[k] : nd->bounds[k + 24]) - o_x) * ridx;
+            const float mny = ((ridy >= 0.0f ? nd->bounds[k + 8] : nd->bounds[k + 32]) - o_y) * ridy;
+            const float mnz = ((ridz >= 0.0f ? nd->bounds[k + 16] : nd->bounds[k + 40]) - o_z) * ridz;
+            const float mxx = ((ridx >= 0.0f ? nd->bounds[k + 24] : nd->bounds[k]) - o_x) * ridx;
+            const float mxy = ((ridy >= 0.0f ? nd->bounds[k + 32] : nd->bounds[k + 8]) - o_y) * ridy;
+            const float mxz = ((ridz >= 0.0f ? nd->bounds[k + 40] : nd->bounds[k + 16]) - o_z) * ridz;
+            const float nn = fmaxf(fmaxf(mnx, mny), fmaxf(mnz, 0.0f));
+            const float ff = fminf(fminf(mxx, mxy), fminf(mxz, dcur));
+            if (nn <= ff) {
+              hit[nh].offset = nd->offset[k];
+              hit[nh].prims = nd->flags[k] == 1 ? nd->num[k] : 0xffffffffu;
+              hit[nh].dist = nn;
+              nh++;
+            }
+            continue;
+          }
           const double nx = ((idx >= 0.0 ? bx0 : bx1) - ox) * idx, fx = ((idx >= 0.0 ? bx1 : bx0) - ox) * idx;
           const double ny = ((idy >= 0.0 ? by0 : by1) - oy) * idy, fy = ((idy >= 0.0 ? by1 : by0) - oy) * idy;
           const double nz = ((idz >= 0.0 ? bz0 : bz1) - oz) * idz, fz = ((idz >= 0.0 ? bz1 : bz0) - oz) * idz;
@@ -240,7 +274,7 @@ void orc_traverse(const orc_node* nodes, const orc_packet* packets, orc_rays* ra
           const orc_packet* k = &packets[index];
           cnt.packets++;
           cnt.triangles += k->num;
-          if (!mode_ties || shadow) {
+          if (!(mode_ties & 1) || shadow) {
             if (packet_vs_ray(k, rays, (size_t)i)) best_packet = index;
           } else {
             /* closest-hit with brute-force tie rule: accept ds == d from a lower packet index */

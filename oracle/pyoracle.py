@@ -36,8 +36,7 @@ def build(target: str = "oracle") -> None:
 
 class Oracle:
     def __init__(self):
-        if not os.path.exists(ORACLE_SO):
-            build("oracle")
+        build("oracle")  # no-op when up to date
         self.lib = L = C.CDLL(ORACLE_SO)
         L.orc_brute_force.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(PhosRays), C.c_uint64]
         L.orc_traverse.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PhosRays), C.c_uint64, C.POINTER(Counters), C.c_int]
@@ -46,6 +45,15 @@ class Oracle:
         L.orc_sizeof_node.restype = C.c_uint32
         L.orc_sizeof_packet.restype = C.c_uint32
         assert L.orc_sizeof_node() == NODE_BYTES and L.orc_sizeof_packet() == PACKET_BYTES
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_create.argtypes = [C.POINTER(PhosSceneDesc)]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_scene_num_lights.argtypes = [C.c_void_p]
+        L.orc_scene_num_lights.restype = C.c_uint32
+        L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_uint32] * 9 + [C.c_uint64, C.c_int, C.c_void_p]
+        L.orc_rnd.restype = C.c_float
+        L.orc_rnd.argtypes = [C.c_uint32] * 5
+        L.orc_film_jitter.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
 
     def brute_force(self, packets: np.ndarray, rays: RayBatch) -> RayBatch:
         out = rays.copy()
@@ -68,6 +76,27 @@ class Oracle:
         m = (C.c_float * 16)(*np.asarray(cam.to_world, np.float32).ravel())
         self.lib.orc_camera_rays(m, cam.fov, cam.film_width, cam.film_height, x0, y0, w, h, jx, jy, C.byref(s))
         return out
+
+
+    def render(self, scene: Scene, nodes: np.ndarray, packets: np.ndarray, spp: int, pps: int = 1, depth: int = 9,
+               seed: int = 0, region=None, spp_range=None, rcp_mode: bool = False, film: np.ndarray | None = None):
+        """Scalar path tracer over a pixel rectangle (default: whole film); returns the RGBA film."""
+        cam = scene.camera
+        d = scene.desc()
+        h = self.lib.orc_scene_create(C.byref(d))
+        if film is None:
+            film = np.zeros((cam.film_height, cam.film_width, 4), np.float32)
+        x0, y0, w, hh = region if region is not None else (0, 0, cam.film_width, cam.film_height)
+        s0, s1 = spp_range if spp_range is not None else (0, spp)
+        self.lib.orc_render(h, nodes.ctypes.data, packets.ctypes.data, x0, y0, w, hh, s0, s1, spp, pps, depth, seed,
+                            1 if rcp_mode else 0, film.ctypes.data)
+        self.lib.orc_scene_destroy(h)
+        return film
+
+    def film_jitter(self, seed: int, spp: int):
+        jx, jy = np.zeros(spp, np.float32), np.zeros(spp, np.float32)
+        self.lib.orc_film_jitter(seed, spp, jx.ctypes.data, jy.ctypes.data)
+        return jx, jy
 
 
 class RefScene:

@@ -91,6 +91,12 @@ void material_t::evaluate(allocator_t& allocator, interaction_t<>* hits, const a
     const auto index = active.index[i];
     shading_result_t result;
     result.bsdf = new (allocator) bsdf_t();
+    // The reference leaves the lobe arrays of a fresh bsdf_t uninitialised (arena memory, src/material.cpp:441-443)
+    // and still samples lobe 0 of a 0-lobe BSDF when a bounce ray lands on an emitter (src/bsdf.cpp:140-153,
+    // SURVEY.md F7): undefined behaviour that replays whatever lobe an earlier hit left at that address.
+    // Zeroing the object freezes that to "type Emissive, weight 0 -> black sample -> the path ends", which is
+    // the behaviour the oracle and the GPU implement.
+    memset((void*)result.bsdf, 0, sizeof(bsdf_t));
     details->closure(hits->n.at(index), result);
     hits->e.from(index, result.e);
     hits->bsdf[index] = result.bsdf;

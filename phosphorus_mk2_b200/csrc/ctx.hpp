@@ -49,6 +49,6 @@ int fail(phos_ctx* ctx, int code, const char* msg);
 bool alloc_rays(phos_ctx* ctx, uint64_t n, phos_rays& out);
 void free_rays(phos_rays& r);
 int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t stream, unsigned long long* cursor,
-                 bool count);
+                 bool count, const uint32_t* n_ptr = nullptr);
 void phos_render_release(phos_ctx* ctx);  // render.cu
 }  // namespace phos

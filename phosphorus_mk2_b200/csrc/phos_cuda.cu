@@ -64,7 +64,7 @@ static void* out_ptr(const phos_rays& r, int k) {
 }
 
 int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t stream, unsigned long long* cursor,
-                 bool count) {
+                 bool count, const uint32_t* n_ptr) {
   if (n == 0) return PHOS_OK;
   TraceArgs a;
   a.rays = dev;
@@ -73,6 +73,7 @@ int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t s
   a.accel.tris = (const uint4*)ctx->d_tris;
   a.cursor = cursor;
   a.counters = ctx->d_counters;
+  a.n_ptr = n_ptr;  // n is then only the capacity that sizes the grid
   if (!cuda_ok(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream), "memset(cursor)")) return PHOS_ERR_CUDA;
   a.tma_ok = 1;  // TMA bulk copies need 16-byte aligned sources
   for (int k = 0; k < 8; ++k) a.tma_ok &= ((uintptr_t)in_ptr(dev, k) & 15u) == 0;

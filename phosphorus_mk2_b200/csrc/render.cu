@@ -2,6 +2,7 @@
 // primary-ray generation, (wavefront shading / NEE / integration / film: see integrate.cuh).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -19,22 +20,18 @@ void phos_render_release(phos_ctx* ctx) {
   ctx->render = nullptr;
 }
 
-// camera::perspective_kernel_t (reference src/kernels/cpu/camera.hpp:78-159), pinhole branch, one
-// thread per pixel of one tile; the film jitter (jx, jy) is shared by every pixel of the sample
-// (src/sampling.cpp:98-111).  Arithmetic in the reference's order with explicit rounding:
+// camera::perspective_kernel_t (reference src/kernels/cpu/camera.hpp:78-159), pinhole branch, for one
+// pixel; the film jitter (jx, jy) is shared by every pixel of the sample (src/sampling.cpp:98-111).
+// Arithmetic in the reference's order with explicit rounding:
 //   ndcx = (x - 0.5) * (1/W) - 0.5 ; ndcy = 0.5 - (y - 0.5) * (1/H)                  (:124-127)
 //   d = ((ndcx + jx/W) * (W/H) * zoom, (ndcy + jy/H) * zoom, -1), normalised          (:132-135)
 //   p = (0,0,0) * M + row 3 ; d = d * M, row-vector convention, mul + two fmadd        (matrix.hpp:58-104)
 // One deliberate difference: normalize() multiplies by _mm256_rcp_ps(sqrt(l)) in the reference
 // (~12-bit, micro-architecture specific, src/math/simd/vector.hpp:126-133); here it is the correctly
 // rounded 1/sqrt(l).
-__global__ void camera_rays_kernel(const DevCamera cam, const phos_tile* __restrict__ tiles,
-                                   const unsigned long long* __restrict__ offsets, float jx, float jy, phos_rays out) {
-  const phos_tile t = tiles[blockIdx.y];
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= t.w * t.h) return;
-  const uint32_t x = k % t.w, y = k / t.w;
-  const float sx = (float)(t.x + x), sy = (float)(t.y + y);
+__device__ __forceinline__ void camera_ray(const DevCamera& cam, uint32_t px, uint32_t py, float jx, float jy, float* o,
+                                           float* w) {
+  const float sx = (float)px, sy = (float)py;
   const float ndcy = __fsub_rn(0.5f, __fmul_rn(__fadd_rn(-0.5f, sy), cam.stepy));
   const float ndcx = __fsub_rn(__fmul_rn(__fadd_rn(-0.5f, sx), cam.stepx), 0.5f);
   float dx = __fmul_rn(__fmul_rn(__fadd_rn(ndcx, __fmul_rn(jx, cam.stepx)), cam.ratio), cam.zoom);
@@ -46,13 +43,28 @@ __global__ void camera_rays_kernel(const DevCamera cam, const phos_tile* __restr
   dy = __fmul_rn(dy, ool);
   dz = __fmul_rn(dz, ool);
   const float* m = cam.m;
+  o[0] = __fadd_rn(__fmaf_rn(0.0f, m[8], __fmaf_rn(0.0f, m[4], __fmul_rn(0.0f, m[0]))), m[12]);
+  o[1] = __fadd_rn(__fmaf_rn(0.0f, m[9], __fmaf_rn(0.0f, m[5], __fmul_rn(0.0f, m[1]))), m[13]);
+  o[2] = __fadd_rn(__fmaf_rn(0.0f, m[10], __fmaf_rn(0.0f, m[6], __fmul_rn(0.0f, m[2]))), m[14]);
+  w[0] = __fmaf_rn(dz, m[8], __fmaf_rn(dy, m[4], __fmul_rn(dx, m[0])));
+  w[1] = __fmaf_rn(dz, m[9], __fmaf_rn(dy, m[5], __fmul_rn(dx, m[1])));
+  w[2] = __fmaf_rn(dz, m[10], __fmaf_rn(dy, m[6], __fmul_rn(dx, m[2])));
+}
+
+__global__ void camera_rays_kernel(const DevCamera cam, const phos_tile* __restrict__ tiles,
+                                   const unsigned long long* __restrict__ offsets, float jx, float jy, phos_rays out) {
+  const phos_tile t = tiles[blockIdx.y];
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t.w * t.h) return;
+  float o[3], w[3];
+  camera_ray(cam, t.x + k % t.w, t.y + k / t.w, jx, jy, o, w);
   const unsigned long long i = offsets[blockIdx.y] + k;
-  out.px[i] = __fadd_rn(__fmaf_rn(0.0f, m[8], __fmaf_rn(0.0f, m[4], __fmul_rn(0.0f, m[0]))), m[12]);
-  out.py[i] = __fadd_rn(__fmaf_rn(0.0f, m[9], __fmaf_rn(0.0f, m[5], __fmul_rn(0.0f, m[1]))), m[13]);
-  out.pz[i] = __fadd_rn(__fmaf_rn(0.0f, m[10], __fmaf_rn(0.0f, m[6], __fmul_rn(0.0f, m[2]))), m[14]);
-  out.wx[i] = __fmaf_rn(dz, m[8], __fmaf_rn(dy, m[4], __fmul_rn(dx, m[0])));
-  out.wy[i] = __fmaf_rn(dz, m[9], __fmaf_rn(dy, m[5], __fmul_rn(dx, m[1])));
-  out.wz[i] = __fmaf_rn(dz, m[10], __fmaf_rn(dy, m[6], __fmul_rn(dx, m[2])));
+  out.px[i] = o[0];
+  out.py[i] = o[1];
+  out.pz[i] = o[2];
+  out.wx[i] = w[0];
+  out.wy[i] = w[1];
+  out.wz[i] = w[2];
   out.d[i] = 3.402823466e+38f;
   out.flags[i] = 0u;
 }
@@ -130,7 +142,145 @@ int phos_cuda_flush_l2(phos_ctx* ctx) {
 
 namespace phos {
 
-int RenderState::upload(phos_ctx*, const phos_scene_desc*) { return PHOS_OK; }
+namespace {
+template <typename T>
+bool to_device(phos_ctx* ctx, RenderState& R, const T* host, size_t count, const T** out) {
+  *out = nullptr;
+  if (count == 0) count = 1;  // keep pointers non-null
+  void* d = nullptr;
+  if (!cuda_ok(ctx, cudaMalloc(&d, count * sizeof(T)), "cudaMalloc(scene)")) return false;
+  R.scene_allocs.push_back(d);
+  if (host && !cuda_ok(ctx, cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice), "upload scene")) return false;
+  *out = (const T*)d;
+  return true;
+}
+
+// microfacet_t::roughness_to_alpha + the precompute clamp (reference src/bsdf/params.hpp:86-99)
+float roughness_to_alpha(float roughness) {
+  roughness = std::max(roughness, (float)1e-5);
+  const float x = std::log(roughness);
+  return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+float tri_area(const float* a, const float* b, const float* c) {  // triangle_t::area (src/mesh.cpp:291-298)
+  const float abx = b[0] - a[0], aby = b[1] - a[1], abz = b[2] - a[2];
+  const float acx = c[0] - a[0], acy = c[1] - a[1], acz = c[2] - a[2];
+  const float zx = aby * acz - abz * acy, zy = abz * acx - abx * acz, zz = abx * acy - aby * acx;
+  return 0.5f * std::sqrt(zx * zx + zy * zy + zz * zz);
+}
+}  // namespace
+
+// What tile_renderer_t reads from scene_t while rendering: geometry for shading normals and light
+// sampling, the closure table, the area lights (one per emissive face set, in mesh -> set order:
+// src/mesh.cpp:108-116, src/scene.cpp:49-55) with their total areas (src/light.cpp:30-45).
+int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
+  const uint32_t nm = d->num_meshes;
+  if (nm == 0 || !d->vert_offset || !d->vertices || !d->face_offset || !d->faces || !d->mesh_smooth || !d->set_offset ||
+      !d->set_material || !d->set_face_offset || !d->set_faces || (d->num_materials && !d->materials))
+    return fail(ctx, PHOS_ERR_INVALID, "incomplete scene description");
+  num_meshes = nm;
+  num_materials = d->num_materials;
+  const size_t nv = d->vert_offset[nm], nf = d->face_offset[nm];
+  for (uint32_t m = 0; m < nm; ++m)
+    if (d->mesh_smooth[m] && !d->normals) return fail(ctx, PHOS_ERR_INVALID, "smooth mesh without vertex normals");
+  const uint32_t nsets = d->set_offset[nm];
+  for (uint32_t s = 0; s < nsets; ++s)
+    if (d->set_material[s] >= d->num_materials) return fail(ctx, PHOS_ERR_INVALID, "face set with an unknown material");
+
+  std::vector<DevMaterial> mats(std::max<uint32_t>(1, d->num_materials));
+  for (uint32_t m = 0; m < d->num_materials; ++m) {
+    const phos_material& in = d->materials[m];
+    DevMaterial& o = mats[m];
+    o.kind = in.kind;
+    if (in.kind > PHOS_MAT_EMITTER) return fail(ctx, PHOS_ERR_INVALID, "material kind outside the built-in closure subset");
+    if (in.kind == PHOS_MAT_GLOSSY && !(in.roughness > 0.0f))
+      return fail(ctx, PHOS_ERR_INVALID, "glossy roughness 0 is the mirror closure, which is outside the built-in subset");
+    for (int k = 0; k < 3; ++k) o.cs[k] = in.cs[k];
+    const float r2 = in.roughness * in.roughness;  // glossy_bsdf_node.osl:26
+    o.alpha = std::min(1.0f, std::max(0.0001f, roughness_to_alpha(r2)));
+    const float k = (float)(in.power / M_PI);  // diffuse_emitter_node.osl:18
+    for (int c = 0; c < 3; ++c) o.e[c] = 1.0f * (k * in.cs[c]);
+  }
+  std::vector<uint32_t> light_first, light_tri_mesh, light_tri_face;
+  std::vector<float> light_area;
+  for (uint32_t m = 0; m < nm; ++m)
+    for (uint32_t s = d->set_offset[m]; s < d->set_offset[m + 1]; ++s) {
+      const uint32_t mat = d->set_material[s];
+      if (d->materials[mat].kind != PHOS_MAT_EMITTER) continue;
+      light_first.push_back((uint32_t)light_tri_mesh.size());
+      float area = 0.0f;
+      for (uint32_t j = d->set_face_offset[s]; j < d->set_face_offset[s + 1]; ++j) {
+        const uint32_t face = d->set_faces[j];
+        if (face >= d->face_offset[m + 1] - d->face_offset[m]) return fail(ctx, PHOS_ERR_INVALID, "face set index out of range");
+        light_tri_mesh.push_back(m | (mat << 16));
+        light_tri_face.push_back(face * 3);
+        const uint32_t* f = d->faces + 3 * ((size_t)d->face_offset[m] + face);
+        const float* v = d->vertices + 3 * (size_t)d->vert_offset[m];
+        area += tri_area(v + 3 * (size_t)f[0], v + 3 * (size_t)f[1], v + 3 * (size_t)f[2]);
+      }
+      light_area.push_back(area);
+    }
+  scene.nlights = (uint32_t)light_area.size();
+  light_first.push_back((uint32_t)light_tri_mesh.size());
+
+  const DevMaterial* dm = nullptr;
+  bool ok = to_device(ctx, *this, d->vertices, 3 * nv, &scene.verts) && to_device(ctx, *this, d->faces, 3 * nf, &scene.faces) &&
+            to_device(ctx, *this, d->vert_offset, (size_t)nm + 1, &scene.vert_offset) &&
+            to_device(ctx, *this, d->face_offset, (size_t)nm + 1, &scene.face_offset) &&
+            to_device(ctx, *this, d->mesh_smooth, (size_t)nm, &scene.mesh_smooth) &&
+            to_device(ctx, *this, mats.data(), mats.size(), &dm) &&
+            to_device(ctx, *this, light_first.data(), light_first.size(), &scene.light_first) &&
+            to_device(ctx, *this, light_area.data(), light_area.size(), &scene.light_area) &&
+            to_device(ctx, *this, light_tri_mesh.data(), light_tri_mesh.size(), &scene.light_tri_mesh) &&
+            to_device(ctx, *this, light_tri_face.data(), light_tri_face.size(), &scene.light_tri_face);
+  scene.mats = dm;
+  scene.normals = nullptr;
+  if (ok && d->normals) ok = to_device(ctx, *this, d->normals, 3 * nv, &scene.normals);
+  if (!ok) return PHOS_ERR_CUDA;
+  const size_t film_bytes = (size_t)camera.width * camera.height * 4 * sizeof(float);
+  if (!cuda_ok(ctx, cudaMalloc(&film, film_bytes), "cudaMalloc(film)") || !cuda_ok(ctx, cudaMemset(film, 0, film_bytes), "clear film"))
+    return PHOS_ERR_CUDA;
+  return PHOS_OK;
+}
+
+bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixels) {
+  if (wf.capacity >= paths && wf.pixel) {
+    // the pixel table is sized by the largest batch seen; regrow below if this one has more pixels
+  }
+  if (wf.capacity < paths || wf.pixel_capacity < pixels) {
+    cudaStreamSynchronize(ctx->stream);
+    release_wavefront();
+    const uint64_t cap = std::max<uint64_t>(paths, 1024);
+    bool ok = alloc_rays(ctx, cap, wf.rays[0]) && alloc_rays(ctx, cap, wf.rays[1]) && alloc_rays(ctx, cap, wf.shadow);
+    auto get = [&](void** p, size_t bytes) { return ok && (ok = cuda_ok(ctx, cudaMalloc(p, bytes), "cudaMalloc(wavefront)")); };
+    get((void**)&wf.slot_path[0], cap * 4);
+    get((void**)&wf.slot_path[1], cap * 4);
+    get((void**)&wf.count, 16);
+    get((void**)&wf.n, cap * 12);
+    get((void**)&wf.light_pdf, cap * 4);
+    get((void**)&wf.beta, cap * 12);
+    get((void**)&wf.rad, cap * 12);
+    get((void**)&wf.depth, cap * 4);
+    get((void**)&wf.pixel, std::max<uint64_t>(pixels, 1024) * 4);
+    if (!ok) {
+      release_wavefront();
+      return false;
+    }
+    wf.capacity = cap;
+    wf.pixel_capacity = std::max<uint64_t>(pixels, 1024);
+  }
+  return true;
+}
+
+void RenderState::release_wavefront() {
+  free_rays(wf.rays[0]);
+  free_rays(wf.rays[1]);
+  free_rays(wf.shadow);
+  void* ptrs[] = {wf.slot_path[0], wf.slot_path[1], wf.count, wf.n, wf.light_pdf, wf.beta, wf.rad, wf.depth, wf.pixel};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  wf = Wavefront();
+}
 
 bool RenderState::set_tiles(phos_ctx* ctx, const phos_tile* tiles, const unsigned long long* offsets, uint32_t n) {
   if (n > tile_capacity) {
@@ -152,6 +302,14 @@ bool RenderState::set_tiles(phos_ctx* ctx, const phos_tile* tiles, const unsigne
 }
 
 void RenderState::release() {
+  release_wavefront();
+  for (void* p : scene_allocs) cudaFree(p);
+  scene_allocs.clear();
+  if (film) cudaFree(film);
+  if (d_jitter) cudaFree(d_jitter);
+  film = nullptr;
+  d_jitter = nullptr;
+  jitter_capacity = 0;
   if (d_tiles) cudaFree(d_tiles);
   if (d_tile_offsets) cudaFree(d_tile_offsets);
   d_tiles = nullptr;

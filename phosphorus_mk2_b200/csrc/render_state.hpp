@@ -3,9 +3,11 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
 
 #include "../../include/phos_cuda.h"
 #include "ctx.hpp"
+#include "integrate.cuh"
 
 namespace phos {
 
@@ -18,14 +20,41 @@ struct DevCamera {
   uint32_t width, height;
 };
 
+// Wavefront state for up to `capacity` concurrent paths (SoA, all in HBM).
+struct Wavefront {
+  uint64_t capacity = 0;
+  uint64_t pixel_capacity = 0;
+  phos_rays rays[2] = {};     // closest-hit ray streams, ping-pong between bounces
+  phos_rays shadow = {};      // next-event shadow-ray stream
+  uint32_t* slot_path[2] = {nullptr, nullptr};  // slot -> path, ping-pong
+  uint32_t* count = nullptr;  // [0..1] live slots of stream 0 / 1 (device counters), [2] scratch
+  float* n = nullptr;         // shading normal per slot, 3 x capacity
+  float* light_pdf = nullptr; // per slot
+  float* beta = nullptr;      // per path, 3 x capacity
+  float* rad = nullptr;       // per path, 3 x capacity
+  uint32_t* depth = nullptr;  // per path
+  uint32_t* pixel = nullptr;  // film pixel (y * W + x) per tile-pixel of the current batch
+};
+
 struct RenderState {
   DevCamera camera;
   phos_tile* d_tiles = nullptr;
   unsigned long long* d_tile_offsets = nullptr;
   uint32_t tile_capacity = 0;
 
+  DevScene scene = {};
+  std::vector<void*> scene_allocs;
+  uint32_t num_meshes = 0, num_materials = 0;
+
+  float* film = nullptr;  // W * H * 4
+  float* d_jitter = nullptr;
+  uint32_t jitter_capacity = 0;
+  Wavefront wf;
+
   int upload(phos_ctx* ctx, const phos_scene_desc* scene);
   bool set_tiles(phos_ctx* ctx, const phos_tile* tiles, const unsigned long long* offsets, uint32_t n);
+  bool ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixels);
+  void release_wavefront();
   void release();
 };
 

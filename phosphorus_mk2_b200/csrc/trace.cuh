@@ -46,6 +46,7 @@ struct TraceArgs {
   unsigned long long* cursor;    // chunk counter (zeroed before launch)
   unsigned long long* counters;  // [2]: nodes visited, triangles tested (kCount only)
   int tma_ok;                    // all eight input arrays are 16-byte aligned
+  const uint32_t* n_ptr;         // when set, the stream length is read from HBM (wavefront queues)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   __shared__ alignas(8) unsigned long long s_bar[kTraceWarps][2];
 
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long N = P.n_ptr ? (unsigned long long)*P.n_ptr : P.n;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint32_t(*stage)[8][kChunk] = s_stage[warp];
   unsigned long long* bar = s_bar[warp];
@@ -108,12 +110,12 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
     if (lane == 0) c = atomicAdd(P.cursor, 1ull);
     c = __shfl_sync(0xffffffffu, c, 0);
     const unsigned long long base = c * kChunk;
-    if (base >= P.n) {
+    if (base >= N) {
       exhausted = true;
       return;
     }
     nxt_base = base;
-    nxt_cnt = (uint32_t)min((unsigned long long)kChunk, P.n - base);
+    nxt_cnt = (uint32_t)min((unsigned long long)kChunk, N - base);
     nxt_tma = P.tma_ok && nxt_cnt == kChunk;
     if (nxt_tma) {
       if (lane == 0) {

@@ -1,0 +1,451 @@
+// wavefront.cu — the wavefront path tracer that replaces the per-thread tile loop of the reference
+// (tile_renderer_t::render_tile / trace_rays, src/xpu/cpu.cpp:148-205) on the device:
+//
+//   paths_init      camera rays + path state for pixels x samples-in-flight            (camera.hpp:78-159)
+//   per bounce:     trace (closest hit)                                                 (trace.cuh)
+//                   shade_nee   interaction, closure, light sample -> shadow-ray queue  (deferred_shading_kernel.hpp,
+//                                                                                        spt.hpp:95-149)
+//                   trace (any hit, the shadow queue)
+//                   integrate   radiance, Russian roulette, BSDF sample, and compaction
+//                               of the survivors into the next ray stream with warp-
+//                               aggregated queue appends (ballot + popc + one atomic)    (spt.hpp:161-328)
+//   film_accumulate radiance / (spp * pps) into the device film                          (cpu.cpp:175-198)
+//
+// Queue lengths live in HBM and every kernel (the traversal kernel included) reads them there, so a
+// whole frame is enqueued without a single host synchronisation.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/phos_cuda.h"
+#include "ctx.hpp"
+#include "render_state.hpp"
+
+namespace phos {
+
+__device__ __forceinline__ void camera_ray_exact(const DevCamera& cam, uint32_t px, uint32_t py, float jx, float jy, float* o,
+                                                 float* w) {
+  // same arithmetic as camera_rays_kernel (render.cu); see the comment there
+  const float sx = (float)px, sy = (float)py;
+  const float ndcy = __fsub_rn(0.5f, __fmul_rn(__fadd_rn(-0.5f, sy), cam.stepy));
+  const float ndcx = __fsub_rn(__fmul_rn(__fadd_rn(-0.5f, sx), cam.stepx), 0.5f);
+  float dx = __fmul_rn(__fmul_rn(__fadd_rn(ndcx, __fmul_rn(jx, cam.stepx)), cam.ratio), cam.zoom);
+  float dy = __fmul_rn(__fadd_rn(ndcy, __fmul_rn(jy, cam.stepy)), cam.zoom);
+  float dz = -1.0f;
+  const float l = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
+  const float ool = __fdiv_rn(1.0f, __fsqrt_rn(l));
+  dx = __fmul_rn(dx, ool);
+  dy = __fmul_rn(dy, ool);
+  dz = __fmul_rn(dz, ool);
+  const float* m = cam.m;
+  o[0] = __fadd_rn(__fmaf_rn(0.0f, m[8], __fmaf_rn(0.0f, m[4], __fmul_rn(0.0f, m[0]))), m[12]);
+  o[1] = __fadd_rn(__fmaf_rn(0.0f, m[9], __fmaf_rn(0.0f, m[5], __fmul_rn(0.0f, m[1]))), m[13]);
+  o[2] = __fadd_rn(__fmaf_rn(0.0f, m[10], __fmaf_rn(0.0f, m[6], __fmul_rn(0.0f, m[2]))), m[14]);
+  w[0] = __fmaf_rn(dz, m[8], __fmaf_rn(dy, m[4], __fmul_rn(dx, m[0])));
+  w[1] = __fmaf_rn(dz, m[9], __fmaf_rn(dy, m[5], __fmul_rn(dx, m[1])));
+  w[2] = __fmaf_rn(dz, m[10], __fmaf_rn(dy, m[6], __fmul_rn(dx, m[2])));
+}
+
+struct FrameArgs {
+  DevCamera cam;
+  DevScene scene;
+  uint32_t P;          // pixels in the batch (all tiles)
+  uint32_t Q;          // paths in flight = P * samples in this batch
+  uint32_t spp_begin;  // first sample index of the batch
+  uint32_t seed;
+  uint32_t max_depth;
+  float scale;  // 1 / (spp_total * pps)
+  const float* jitter;  // [2 * spp_total]: jx then jy
+  const uint32_t* pixel;
+  float* beta;
+  float* rad;
+  uint32_t* depth;
+  float* n;
+  float* light_pdf;
+  uint32_t* count;  // [2]
+};
+
+// film pixel id of every tile-pixel of the batch: slot order = tile after tile, row-major inside
+__global__ void pixel_table_kernel(const phos_tile* __restrict__ tiles, const unsigned long long* __restrict__ offsets, uint32_t W,
+                                   uint32_t* __restrict__ pixel) {
+  const phos_tile t = tiles[blockIdx.y];
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t.w * t.h) return;
+  pixel[offsets[blockIdx.y] + k] = (t.y + k / t.w) * W + (t.x + k % t.w);
+}
+
+// prepare_sample (cpu.cpp:116-131): path q = (sample q / P, pixel q % P) starts in slot q
+__global__ void paths_init_kernel(const FrameArgs A, phos_rays rays, uint32_t* __restrict__ slot_path) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0) {
+    A.count[0] = A.Q;
+    A.count[1] = 0u;
+  }
+  if (q >= A.Q) return;
+  const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P];
+  float o[3], w[3];
+  camera_ray_exact(A.cam, pix % A.cam.width, pix / A.cam.width, A.jitter[2 * s], A.jitter[2 * s + 1], o, w);
+  rays.px[q] = o[0];
+  rays.py[q] = o[1];
+  rays.pz[q] = o[2];
+  rays.wx[q] = w[0];
+  rays.wy[q] = w[1];
+  rays.wz[q] = w[2];
+  rays.d[q] = 3.402823466e+38f;
+  rays.flags[q] = 0u;
+  slot_path[q] = q;
+  A.beta[q] = 1.0f;
+  A.beta[q + (size_t)A.Q] = 1.0f;
+  A.beta[q + 2 * (size_t)A.Q] = 1.0f;
+  A.rad[q] = 0.0f;
+  A.rad[q + (size_t)A.Q] = 0.0f;
+  A.rad[q + 2 * (size_t)A.Q] = 0.0f;
+  A.depth[q] = 0u;
+}
+
+// Interaction + next-event shadow ray for every live slot: build_interactions
+// (deferred_shading_kernel.hpp:39-72), fresh_light_samples (sampling.cpp:160-180), area_light_t::sample
+// (light.cpp:47-71), light_sampler_t (spt.hpp:116-148).
+__global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const uint32_t* __restrict__ slot_path, int cur,
+                                 phos_rays sh) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.count[cur]) return;
+  const uint32_t flags = rays.flags[i];
+  if (!(flags & PHOS_HIT) || A.scene.nlights == 0u) {  // a missed slot gets a masked query (spt.hpp:139-143)
+    sh.flags[i] = PHOS_SHADOW | PHOS_MASKED;
+    if (!(flags & PHOS_HIT)) return;
+  }
+  const v3 o = V(rays.px[i], rays.py[i], rays.pz[i]), w = V(rays.wx[i], rays.wy[i], rays.wz[i]);
+  const uint32_t mm = rays.mesh[i], face = rays.face[i];
+  const v3 P = add(o, scl(w, rays.d[i]));  // hits->p = p + wi * d
+  const v3 n = shading_normal(A.scene, mm & 0xffffu, face, rays.u[i], rays.v[i]);
+  A.n[i] = n.x;
+  A.n[i + (size_t)A.Q] = n.y;
+  A.n[i + 2 * (size_t)A.Q] = n.z;
+  if (A.scene.nlights == 0u) return;
+
+  const uint32_t q = slot_path[i];
+  const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P], depth = A.depth[q];
+  const uint32_t nl = A.scene.nlights;
+  const float xl = rng(A.seed, pix, s, depth, DIM_LIGHT);
+  const uint32_t l = (uint32_t)fminf(floorf(xl * nl), (float)(nl - 1));
+  const float ux = rng(A.seed, pix, s, depth, DIM_LIGHT_U), uy = rng(A.seed, pix, s, depth, DIM_LIGHT_V);
+  const uint32_t first = A.scene.light_first[l], num = A.scene.light_first[l + 1] - first;
+  uint32_t k = (uint32_t)floorf(ux * num);  // uniform by index, pdf 1 / area (light.cpp:55,67)
+  if (k > num - 1) k = num - 1;
+  const float remapped = fminf(ux * num - k, 1.0f - FLT_EPSILON);
+  const float sq = sqrtf(remapped);  // triangle_t::sample (mesh.cpp:318-324)
+  const float bu = 1 - sq, bv = uy * sq;
+  const uint32_t lm = A.scene.light_tri_mesh[first + k], lf = A.scene.light_tri_face[first + k];
+  const v3 a = scene_vert(A.scene, lm & 0xffffu, lf, 0), b = scene_vert(A.scene, lm & 0xffffu, lf, 1),
+           c = scene_vert(A.scene, lm & 0xffffu, lf, 2);
+  const v3 L = add(add(scl(a, bu), scl(b, bv)), scl(c, 1 - bu - bv));  // barycentric_to_point (mesh.cpp:314-316)
+  A.light_pdf[i] = (1.0f / A.scene.light_area[l]) / nl;
+  const v3 so = add(P, scl(n, 0.0001f));  // simd::offset
+  v3 wi = sub(L, so);
+  const float l2 = __fmaf_rn(wi.x, wi.x, __fmaf_rn(wi.y, wi.y, __fmul_rn(wi.z, wi.z)));
+  const float dist = sqrtf(l2) - 0.0001f;
+  const float ool = 1.0f / sqrtf(l2);  // the reference multiplies by the ~12-bit rcpps here (simd/vector.hpp:126-133)
+  wi = V(wi.x * ool, wi.y * ool, wi.z * ool);
+  const bool ish = __fmaf_rn(n.x, wi.x, __fmaf_rn(n.y, wi.y, __fmul_rn(n.z, wi.z))) >= 0.0f;  // simd::in_same_hemisphere
+  sh.px[i] = so.x;
+  sh.py[i] = so.y;
+  sh.pz[i] = so.z;
+  sh.wx[i] = wi.x;
+  sh.wy[i] = wi.y;
+  sh.wz[i] = wi.z;
+  sh.d[i] = dist;
+  sh.mesh[i] = lm;  // the sampled light's ids ride on the shadow ray (spt.hpp:120-124)
+  sh.face[i] = lf;
+  sh.u[i] = bu;
+  sh.v[i] = bv;
+  sh.flags[i] = ish ? PHOS_SHADOW : (PHOS_SHADOW | PHOS_MASKED);
+}
+
+// integrator_t::operator() (spt.hpp:161-210) with li (:212-255), sample_bsdf (:257-305) and
+// terminate_path (:307-328); survivors are appended to the next ray stream.
+__global__ void integrate_kernel(const FrameArgs A, const phos_rays rays, const phos_rays sh,
+                                 const uint32_t* __restrict__ slot_path, int cur, phos_rays next, uint32_t* __restrict__ next_path) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < A.count[cur];
+  bool alive = false;
+  uint32_t q = 0;
+  v3 no = V(0, 0, 0), nw = V(0, 0, 0);
+  if (valid && (rays.flags[i] & PHOS_HIT)) {  // a miss adds beta * e_env = 0 (no environment in the subset)
+    q = slot_path[i];
+    const size_t Q = A.Q;
+    const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P];
+    uint32_t depth = A.depth[q];
+    v3 beta = V(A.beta[q], A.beta[q + Q], A.beta[q + 2 * Q]);
+    v3 rad = V(A.rad[q], A.rad[q + Q], A.rad[q + 2 * Q]);
+    const v3 o = V(rays.px[i], rays.py[i], rays.pz[i]), w = V(rays.wx[i], rays.wy[i], rays.wz[i]);
+    const v3 P = add(o, scl(w, rays.d[i]));
+    const v3 wo = neg(w);
+    const v3 n = V(A.n[i], A.n[i + Q], A.n[i + 2 * Q]);
+    const uint32_t mat = rays.mesh[i] >> 16;
+    const DevMaterial mt = A.scene.mats[mat];
+    const bool emitter = mt.kind == PHOS_MAT_EMITTER;
+    const v3 cs = V(mt.cs[0], mt.cs[1], mt.cs[2]);
+    if (emitter && (depth == 0 || (rays.flags[i] & PHOS_SPECULAR))) rad = add(rad, mul(beta, V(mt.e[0], mt.e[1], mt.e[2])));
+    const uint32_t sflags = sh.flags[i];
+    if (!(sflags & (PHOS_HIT | PHOS_MASKED)) && !emitter) {  // li(): a 0-lobe BSDF evaluates to 0
+      const v3 swi = V(sh.wx[i], sh.wy[i], sh.wz[i]);
+      const float atl = dot(n, swi);
+      if (atl * dot(n, wo) > 0.0f) {  // reflective lobes need wi and wo on the same side (bsdf.cpp:122-127)
+        const float ev = mt.kind == PHOS_MAT_DIFFUSE ? (float)PHOS_1_PI : ct_f(n, mt.alpha, mt.alpha, swi, wo);
+        const uint32_t lm = sh.mesh[i];
+        const v3 light_n = shading_normal(A.scene, lm & 0xffffu, sh.face[i], sh.u[i], sh.v[i]);
+        const DevMaterial lmt = A.scene.mats[lm >> 16];
+        const float sd = sh.d[i];
+        const float pdf = A.light_pdf[i] * sd * sd / fabsf(dot(light_n, neg(swi)));
+        const v3 f = scl(mul(V(ev, ev, ev), cs), atl);                                      // e * weight * atl
+        const v3 li = scl(mul(scl(V(lmt.e[0], lmt.e[1], lmt.e[2]), 4), f), 1.0f / pdf);    // (light.e * 4) * f * (1 / pdf)
+        rad = add(rad, mul(beta, li));
+      }
+    }
+    ++depth;
+    // terminate_path
+    float wgt = 1.0f;
+    alive = depth < A.max_depth;
+    if (alive && depth >= 3) {
+      const float yb = 0.212671f * beta.x + 0.715160f * beta.y + 0.072169f * beta.z;
+      const float qq = fmaxf(0.05f, 1.0f - yb);
+      alive = rng(A.seed, pix, s, depth - 1, DIM_RR) >= qq;
+      if (alive) wgt = (1.0f / (1.0f - qq));
+    }
+    beta = scl(beta, wgt);
+    if (alive && emitter) alive = false;  // 0-lobe BSDF: the path ends on an emitter
+    if (alive) {
+      // bsdf_t::sample with a single lobe: index 0, u = min(sample.x, 1 - eps) (bsdf.cpp:140-148)
+      const float su = fminf(rng(A.seed, pix, s, depth - 1, DIM_BSDF_U) * 1 - 0, 1.0f - FLT_EPSILON);
+      const float sv = rng(A.seed, pix, s, depth - 1, DIM_BSDF_V);
+      v3 sampled = V(0, 0, 0);
+      float pdf = 0.0f, fv;
+      if (mt.kind == PHOS_MAT_DIFFUSE) {  // lambert::sample + sample::hemisphere::cosine_weighted
+        const Base base = make_base(n);
+        const float rr = sqrtf(su);
+        const float theta = (float)(2 * PHOS_PI * sv);
+        const float x = rr * cosf(theta), y = rr * sinf(theta);
+        const v3 lo = V(x, sqrtf(fmaxf(0.0f, 1.0f - su)), y);
+        pdf = lo.y * (float)(1.0f / PHOS_PI);
+        sampled = to_world(base, lo);
+        fv = (float)PHOS_1_PI;
+      } else {
+        fv = ct_sample(n, mt.alpha, mt.alpha, wo, sampled, su, sv, pdf);
+        if (fv == 0.0f) alive = false;
+      }
+      if (pdf == 0.0f) alive = false;
+      const v3 f = V(fv * cs.x, fv * cs.y, fv * cs.z);
+      if (f.x == 0.0f && f.y == 0.0f && f.z == 0.0f) alive = false;
+      if (alive) {
+        const float weight = dot(n, sampled);
+        beta = mul(beta, scl(f, fabsf(weight) / pdf));
+        no = add(P, scl(n, weight < 0.0f ? -0.0001f : 0.0001f));  // offset() (math/vector.hpp:14-21)
+        nw = sampled;
+      }
+    }
+    A.depth[q] = depth;
+    A.beta[q] = beta.x;
+    A.beta[q + Q] = beta.y;
+    A.beta[q + 2 * Q] = beta.z;
+    A.rad[q] = rad.x;
+    A.rad[q + Q] = rad.y;
+    A.rad[q + 2 * Q] = rad.z;
+  }
+  // compaction: one atomic per warp reserves slots for all its survivors
+  const unsigned live = __ballot_sync(0xffffffffu, alive);
+  if (live == 0u) return;
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if (lane == (unsigned)(__ffs(live) - 1)) base = atomicAdd(&A.count[cur ^ 1], (uint32_t)__popc(live));
+  base = __shfl_sync(0xffffffffu, base, __ffs(live) - 1);
+  if (alive) {
+    const uint32_t slot = base + __popc(live & ((1u << lane) - 1u));
+    next.px[slot] = no.x;
+    next.py[slot] = no.y;
+    next.pz[slot] = no.z;
+    next.wx[slot] = nw.x;
+    next.wy[slot] = nw.y;
+    next.wz[slot] = nw.z;
+    next.d[slot] = 3.402823466e+38f;
+    next.flags[slot] = 0u;  // neither lobe of the subset is SPECULAR
+    next_path[slot] = q;
+  }
+}
+
+// channels.primary->add(x, y, r * (1 / (spp * pps))) per sample (cpu.cpp:175-198), samples in order
+__global__ void film_accumulate_kernel(const FrameArgs A, float* __restrict__ film) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.P) return;
+  float* px = film + 4 * (size_t)A.pixel[t];
+  float r = px[0], g = px[1], b = px[2];
+  for (uint32_t q = t; q < A.Q; q += A.P) {
+    r += A.rad[q] * A.scale;
+    g += A.rad[q + (size_t)A.Q] * A.scale;
+    b += A.rad[q + 2 * (size_t)A.Q] * A.scale;
+  }
+  px[0] = r;
+  px[1] = g;
+  px[2] = b;
+  px[3] = 1.0f;
+}
+
+__global__ void zero_u32_kernel(uint32_t* p) { *p = 0u; }
+
+// sample::stratified_2d (math/sampling.hpp:67-82) as sampler_t::preprocess uses it (sampling.cpp:96-99):
+// one film jitter per sample index, spd = lround(sqrt(spp)) strata per axis.  Entries >= spd^2 are
+// uninitialised in the reference (and spd^2 > spp overruns its array); 0.5 here.
+void film_jitter(uint32_t seed, uint32_t spp, std::vector<float>& out) {
+  out.assign(2 * (size_t)spp, 0.5f);
+  const uint32_t num = (uint32_t)lroundf(sqrtf((float)spp));
+  const float step = 1.0f / (float)num;
+  float dy = 0.0f;
+  uint32_t call = 0;
+  for (uint32_t i = 0; i < num; ++i, dy += step) {
+    float dx = 0.0f;
+    for (uint32_t j = 0; j < num; ++j, dx += step) {
+      const float a = rng(seed, 0xffffffffu, call++, 0, DIM_FILM);
+      const float b = rng(seed, 0xffffffffu, call++, 0, DIM_FILM);
+      if (j * num + i < spp) {
+        out[2 * (size_t)(j * num + i)] = dx + a * step;
+        out[2 * (size_t)(j * num + i) + 1] = dy + b * step;
+      }
+    }
+  }
+}
+
+}  // namespace phos
+
+using namespace phos;
+
+extern "C" {
+
+int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, uint32_t spp_begin, uint32_t spp_end,
+                     uint32_t spp_total, uint64_t seed64) {
+  if (!ctx || !tiles) return PHOS_ERR_INVALID;
+  if (!ctx->render || !ctx->render->film) return fail(ctx, PHOS_ERR_INVALID, "render before upload_scene");
+  if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "render before upload_accel");
+  if (spp_begin >= spp_end || spp_end > spp_total) return fail(ctx, PHOS_ERR_INVALID, "bad sample range");
+  if (n_tiles == 0) return PHOS_OK;
+  cudaSetDevice(ctx->device);
+  RenderState& R = *ctx->render;
+  const uint32_t seed = (uint32_t)(seed64 ^ (seed64 >> 32));
+
+  std::vector<unsigned long long> offsets(n_tiles);
+  unsigned long long total = 0;
+  uint32_t max_px = 0;
+  for (uint32_t i = 0; i < n_tiles; ++i) {
+    if (tiles[i].x + tiles[i].w > R.camera.width || tiles[i].y + tiles[i].h > R.camera.height)
+      return fail(ctx, PHOS_ERR_INVALID, "tile outside the film");
+    offsets[i] = total;
+    total += (unsigned long long)tiles[i].w * tiles[i].h;
+    max_px = std::max(max_px, tiles[i].w * tiles[i].h);
+  }
+  if (total == 0) return PHOS_OK;
+  if (total > 0x7fffffffull) return fail(ctx, PHOS_ERR_INVALID, "too many pixels in one render call");
+  const uint32_t P = (uint32_t)total;
+  // samples in flight: enough paths to fill the machine, bounded by the wavefront's memory
+  const uint64_t target = 4ull << 20;
+  uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(spp_end - spp_begin, target / P));
+  if (!R.ensure_wavefront(ctx, (uint64_t)P * batch, P)) return PHOS_ERR_CUDA;
+  if (!R.set_tiles(ctx, tiles, offsets.data(), n_tiles)) return PHOS_ERR_CUDA;
+  Wavefront& W = R.wf;
+  cudaStream_t st = ctx->stream;
+
+  for (uint32_t first = 0; first < n_tiles; first += 65535) {
+    const uint32_t cnt = std::min<uint32_t>(65535, n_tiles - first);
+    pixel_table_kernel<<<dim3((max_px + 255) / 256, cnt), 256, 0, st>>>(R.d_tiles + first, R.d_tile_offsets + first, R.camera.width,
+                                                                         W.pixel);
+    ctx->launches++;
+  }
+  // film jitter table for this (seed, spp_total)
+  {
+    std::vector<float> jit;
+    film_jitter(seed, spp_total, jit);
+    if (R.jitter_capacity < spp_total) {
+      cudaStreamSynchronize(st);
+      if (R.d_jitter) cudaFree(R.d_jitter);
+      R.d_jitter = nullptr;
+      if (!cuda_ok(ctx, cudaMalloc(&R.d_jitter, 2 * sizeof(float) * spp_total), "cudaMalloc(jitter)")) return PHOS_ERR_CUDA;
+      R.jitter_capacity = spp_total;
+    }
+    if (!cuda_ok(ctx, cudaMemcpyAsync(R.d_jitter, jit.data(), 2 * sizeof(float) * spp_total, cudaMemcpyHostToDevice, st), "upload jitter"))
+      return PHOS_ERR_CUDA;
+    cudaStreamSynchronize(st);  // jit goes out of scope
+  }
+
+  FrameArgs A;
+  A.cam = R.camera;
+  A.scene = R.scene;
+  A.P = P;
+  A.seed = seed;
+  A.max_depth = ctx->opt.path_depth;
+  A.scale = 1.0f / (float)(spp_total * ctx->opt.paths_per_sample);
+  A.jitter = R.d_jitter;
+  A.pixel = W.pixel;
+  A.beta = W.beta;
+  A.rad = W.rad;
+  A.depth = W.depth;
+  A.n = W.n;
+  A.light_pdf = W.light_pdf;
+  A.count = W.count;
+
+  for (uint32_t s0 = spp_begin; s0 < spp_end; s0 += batch) {
+    const uint32_t ns = std::min(batch, spp_end - s0);
+    A.Q = P * ns;
+    A.spp_begin = s0;
+    const uint32_t blocks = (A.Q + 255) / 256;
+    paths_init_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.slot_path[0]);
+    ctx->launches++;
+    for (uint32_t b = 0; b < A.max_depth; ++b) {
+      const int cur = (int)(b & 1u);
+      zero_u32_kernel<<<1, 1, 0, st>>>(W.count + (cur ^ 1));
+      ctx->launches++;
+      int rc = launch_trace(ctx, W.rays[cur], A.Q, st, ctx->d_counters + 24, false, W.count + cur);
+      if (rc) return rc;
+      shade_nee_kernel<<<blocks, 256, 0, st>>>(A, W.rays[cur], W.slot_path[cur], cur, W.shadow);
+      ctx->launches++;
+      rc = launch_trace(ctx, W.shadow, A.Q, st, ctx->d_counters + 25, false, W.count + cur);
+      if (rc) return rc;
+      integrate_kernel<<<blocks, 256, 0, st>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1]);
+      ctx->launches++;
+    }
+    film_accumulate_kernel<<<(P + 255) / 256, 256, 0, st>>>(A, R.film);
+    ctx->launches++;
+  }
+  return cuda_ok(ctx, cudaGetLastError(), "render launch") ? PHOS_OK : PHOS_ERR_CUDA;
+}
+
+int phos_cuda_film_clear(phos_ctx* ctx) {
+  if (!ctx || !ctx->render || !ctx->render->film) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t bytes = (size_t)ctx->render->camera.width * ctx->render->camera.height * 4 * sizeof(float);
+  return cuda_ok(ctx, cudaMemsetAsync(ctx->render->film, 0, bytes, ctx->stream), "film_clear") ? PHOS_OK : PHOS_ERR_CUDA;
+}
+
+int phos_cuda_film_device_ptr(phos_ctx* ctx, void** out_ptr, uint64_t* out_floats) {
+  if (!ctx || !ctx->render || !ctx->render->film || !out_ptr) return PHOS_ERR_INVALID;
+  *out_ptr = ctx->render->film;
+  if (out_floats) *out_floats = (uint64_t)ctx->render->camera.width * ctx->render->camera.height * 4;
+  return PHOS_OK;
+}
+
+int phos_cuda_film_read(phos_ctx* ctx, float* rgba, uint32_t x, uint32_t y, uint32_t w, uint32_t h) {
+  if (!ctx || !ctx->render || !ctx->render->film || !rgba) return PHOS_ERR_INVALID;
+  const DevCamera& c = ctx->render->camera;
+  if (x + w > c.width || y + h > c.height) return fail(ctx, PHOS_ERR_INVALID, "rectangle outside the film");
+  if (w == 0 || h == 0) return PHOS_OK;
+  cudaSetDevice(ctx->device);
+  const float* src = ctx->render->film + 4 * ((size_t)y * c.width + x);
+  if (!cuda_ok(ctx,
+               cudaMemcpy2DAsync(rgba, (size_t)w * 16, src, (size_t)c.width * 16, (size_t)w * 16, h, cudaMemcpyDeviceToHost, ctx->stream),
+               "film_read") ||
+      !cuda_ok(ctx, cudaStreamSynchronize(ctx->stream), "film_read sync"))
+    return PHOS_ERR_CUDA;
+  return PHOS_OK;
+}
+
+}  // extern "C"

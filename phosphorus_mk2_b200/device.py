@@ -178,12 +178,35 @@ class CudaDevice:
     def upload_scene(self, scene: Scene) -> None:
         d = scene.desc()
         self._check(self._L.phos_cuda_upload_scene(self._ctx, C.byref(d)))
+        self._film_wh = (scene.camera.film_width, scene.camera.film_height)
 
     def camera_rays(self, tiles, rays: DeviceRays, jx: float = 0.5, jy: float = 0.5) -> None:
         """camera::perspective_kernel_t over a list of (x, y, w, h) tiles into a device stream."""
         arr = tile_array(tiles)
         assert sum(t[2] * t[3] for t in tiles) <= rays.n
         self._check(self._L.phos_cuda_camera_rays(self._ctx, arr, len(tiles), jx, jy, C.byref(rays.s)))
+
+    def render(self, tiles, spp_begin: int, spp_end: int, spp_total: int, seed: int = 0) -> None:
+        """tile_renderer_t::render_tile over a tile list (src/xpu/cpu.cpp:156-205): accumulate samples
+        [spp_begin, spp_end) of the tiles' pixels into the device film.  Asynchronous."""
+        arr = tile_array(tiles)
+        self._check(self._L.phos_cuda_render(self._ctx, arr, len(tiles), spp_begin, spp_end, spp_total, seed))
+
+    def film_clear(self) -> None:
+        self._check(self._L.phos_cuda_film_clear(self._ctx))
+
+    def film_read(self, x: int = 0, y: int = 0, w: int | None = None, h: int | None = None) -> np.ndarray:
+        """The RGBA float tile buffer film_t<>::add_tile would receive for the rectangle."""
+        w = self._film_wh[0] - x if w is None else w
+        h = self._film_wh[1] - y if h is None else h
+        out = np.zeros((h, w, 4), np.float32)
+        self._check(self._L.phos_cuda_film_read(self._ctx, out.ctypes.data, x, y, w, h))
+        return out
+
+    def film_device_ptr(self) -> tuple[int, int]:
+        p, n = C.c_void_p(0), C.c_uint64(0)
+        self._check(self._L.phos_cuda_film_device_ptr(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def flush_l2(self) -> None:
         self._check(self._L.phos_cuda_flush_l2(self._ctx))

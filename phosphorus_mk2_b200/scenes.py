@@ -83,7 +83,7 @@ def cornell_box(width: int = 512, height: int = 512) -> Scene:
     # two face sets -> two area lights (one light per emissive face set, src/mesh.cpp:108-116)
     s.add(Mesh(np.array(v), np.array(f), [(light, np.arange(0, 2)), (light, np.arange(2, 4))]))
 
-    cam = Camera(fov=math.radians(39.3), film_width=width, film_height=height)
+    cam = Camera(fov=math.radians(65.0), film_width=width, film_height=height)  # reference NDC spans +-0.5: = 39 deg conventional
     m = np.eye(4, dtype=np.float32)
     m[3, :3] = (0.0, 1.0, 3.8)
     cam.to_world = m
