@@ -150,6 +150,111 @@ def run_reference_arm(args, scene, label):
     print(json.dumps(line), flush=True)
 
 
+def run_render_bench(args, scene, label):
+    """Path-traced samples/s: a step = one frame of --spp samples per pixel at --depth, the frame split
+    over the ranks by tiles (or sample ranges), one NCCL film reduce per frame inside the timed region."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cam = scene.camera
+    n_px = cam.film_width * cam.film_height
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle.pyoracle import RefLib
+        ref = RefLib()
+        rs = ref.scene(scene)
+        spp = 4 if n_px > 512 * 512 else 16  # bounded sample: the CPU renderer at a reduced, perfect-square spp
+        secs = []
+        for i in range(args.warmup + args.steps):
+            _, s_ = rs.render(spp, 1, args.depth, single_threaded=False)
+            if i >= args.warmup:
+                secs.append(s_)
+        v = n_px * spp * len(secs) / sum(secs)
+        print(json.dumps({"impl": "reference", "metric": "path-traced samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": label, "spp": spp, "depth": args.depth, "pixels": n_px},
+                          "cpu_baseline": {"value": v, "unit": "samples/s", "cores": ref.hardware_concurrency(), "kind": "reference",
+                                           "sample": f"{spp} spp frame (reference cpu_t::start/join, all host threads)"},
+                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
+    from phosphorus_mk2_b200.frame import film_tensor, reduce_film, samples_of_rank, tiles_of_rank
+    dev = CudaDevice.make(Options(samples_per_pixel=args.spp, paths_per_sample=1, path_depth=args.depth), local)
+    acc = Accel(scene)
+    dev.preprocess(scene, acc)
+    dev.upload_scene(scene)
+    tiles = tile_order_tiles(cam)
+    if args.partition == "tiles":
+        my_tiles, my_range = tiles_of_rank(tiles, rank, world), (0, args.spp)
+    else:
+        my_tiles, my_range = tiles, samples_of_rank(args.spp, rank, world)
+    film_t = film_tensor(dev) if dist else None
+
+    def frame(read_back: bool):
+        dev.film_clear()
+        if my_range[1] > my_range[0] and my_tiles:
+            dev.render(my_tiles, my_range[0], my_range[1], args.spp, seed=1)
+        dev.synchronize()
+        if dist:
+            reduce_film(film_t, dist, 0)
+            import torch
+            torch.cuda.synchronize()
+        if read_back and rank == 0:
+            return dev.film_read()
+        return None
+
+    for _ in range(args.warmup):
+        frame(False)
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = dev.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame(False)
+    if dist:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    launches = dev.launch_count() - l0
+    t0 = time.perf_counter()
+    img = None
+    for _ in range(max(1, args.steps // 2)):
+        img = frame(True)
+    if dist:
+        dist.barrier()
+    dt_e2e = (time.perf_counter() - t0) / max(1, args.steps // 2)
+    if dist:
+        import torch
+        t = torch.tensor([dt, dt_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = float(t[0]), float(t[1])
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        v = n_px * args.spp * args.steps / dt
+        print(json.dumps({"metric": "path-traced samples/s", "value": v, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": label, "spp": args.spp, "depth": args.depth, "pixels": n_px, "partition": args.partition,
+                                     "timing": "wall clock around K frames (render + NCCL film reduce), barrier + sync both sides"},
+                          "clocks": clocks, "gpu_launches": int(launches),
+                          "e2e": {"value": n_px * args.spp / dt_e2e, "unit": "samples/s", "h2d_bytes_per_step": 16 * len(my_tiles) + 8 * args.spp,
+                                  "d2h_bytes_per_step": 16 * n_px},
+                          "image_mean": float(img[..., :3].mean()) if img is not None else None}), flush=True)
+    dev.close()
+    if dist:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,10 +263,17 @@ def main():
     ap.add_argument("--workload", default="spheres")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--render", action="store_true", help="path-traced samples/s (BASELINE configs[0]/[3]) instead of Mrays/s")
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--partition", default="tiles", choices=["tiles", "samples"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     scene, label = make_workload(args.workload)
+    if args.render:
+        run_render_bench(args, scene, label)
+        return
     if args.impl == "reference":
         run_reference_arm(args, scene, label)
         return

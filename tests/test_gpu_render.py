@@ -95,3 +95,44 @@ def test_render_call_order_errors():
     with pytest.raises(PhosError):
         dev.render([(0, 0, 8, 8)], 2, 1, 4)  # bad sample range
     dev.close()
+
+
+def test_start_join_feeds_every_tile_to_the_film_sink():
+    """xpu_t::start / join over the shared tile queue and the film_t<>::add_tile hand-off."""
+    from phosphorus_mk2_b200.frame import FrameState, MemoryFilm, Tiles, join, start
+    sc = scenes.cornell_box(96, 80)
+    acc = Accel(sc)
+    direct, _ = render_gpu(sc, acc, 4, 4, 9)
+    dev = CudaDevice.make(Options(4, 1, 4), 0)
+    dev.preprocess(sc, acc)
+    dev.upload_scene(sc)
+    tiles = Tiles.make(96, 80)
+    film = MemoryFilm(96, 80)
+    h = start(dev, sc, FrameState(tiles, film, spp=4, seed=9), chunk_tiles=4)
+    join(h)
+    dev.close()
+    assert film.tiles_added == tiles.size
+    assert np.array_equal(film.rgba, direct)
+
+
+def test_two_contexts_emulate_two_ranks():
+    """The multi-GPU frame on one GPU: two contexts each render their share (tile-partitioned, then
+    sample-partitioned); the sum of the two films — what the NCCL reduce computes — is the frame."""
+    from phosphorus_mk2_b200.frame import samples_of_rank, tiles_of_rank
+    sc = scenes.cornell_box(96, 96)
+    acc = Accel(sc)
+    whole, _ = render_gpu(sc, acc, 16, 5, 21)
+    tiles = make_tiles(96, 96)
+    for mode in ("tiles", "samples"):
+        films = []
+        for r in range(2):
+            if mode == "tiles":
+                img, _ = render_gpu(sc, acc, 16, 5, 21, tiles=tiles_of_rank(tiles, r, 2))
+            else:
+                img, _ = render_gpu(sc, acc, 16, 5, 21, ranges=[samples_of_rank(16, r, 2)])
+            films.append(img)
+        total = films[0] + films[1]
+        if mode == "tiles":
+            assert np.array_equal(total[..., :3], whole[..., :3])  # disjoint tiles: the sum is a gather
+        else:
+            assert np.allclose(total[..., :3], whole[..., :3], rtol=2e-6, atol=1e-7)  # (a + b) + (c + d) vs a + b + c + d
