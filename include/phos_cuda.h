@@ -160,6 +160,13 @@ int phos_cuda_camera_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tile
 int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, uint32_t spp_begin, uint32_t spp_end,
                      uint32_t spp_total, uint64_t seed);
 
+/* The ray streams of a path-traced frame, produced by the pipeline itself (BASELINE config 3's ray
+ * sets): run one bounce of sample `sample` over the tiles and copy into `device_out` (capacity >= number
+ * of tile pixels) either the BSDF-sampled bounce rays from the primary hits, compacted (which = 0), or the
+ * next-event shadow rays, one per primary slot, SHADOW or SHADOW|MASKED (which = 1).  Blocking. */
+int phos_cuda_wavefront_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, uint32_t sample, uint32_t spp_total,
+                             uint64_t seed, int which, const phos_rays* device_out, uint64_t capacity, uint64_t* out_count);
+
 /* ---- film: the film_t<>::add_tile hand-off (src/film.hpp:10-16) -------------------------------------- */
 int phos_cuda_film_clear(phos_ctx* ctx);
 /* device pointer of the W*H*4 float film (for the per-frame NCCL reduce done by the caller) */

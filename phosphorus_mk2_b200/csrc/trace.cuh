@@ -21,7 +21,7 @@ namespace phos {
 
 // tuning knobs (defaults chosen by tools/sweep.py runs on the B200, see profiles/)
 #ifndef PHOS_CHUNK
-#define PHOS_CHUNK 64
+#define PHOS_CHUNK 32
 #endif
 #ifndef PHOS_REFILL_MIN
 #define PHOS_REFILL_MIN 6
@@ -30,7 +30,10 @@ namespace phos {
 #define PHOS_TRI_BIAS 2
 #endif
 #ifndef PHOS_MIN_BLOCKS
-#define PHOS_MIN_BLOCKS 6
+#define PHOS_MIN_BLOCKS 7
+#endif
+#ifndef PHOS_TRI_PAIR
+#define PHOS_TRI_PAIR 0
 #endif
 #ifndef PHOS_PREFETCH
 #define PHOS_PREFETCH 0
@@ -162,62 +165,66 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   uint32_t n_nodes = 0, n_tris = 0;
 
   for (;;) {
-    // 1. retire finished rays
-    if (has_ray && (trem | lmask) == 0u && (cur.y >> 8) == 0u && st.sp == 0) {
-      if (changed) {
-        P.rays.d[ridx] = r.d;
-        P.rays.flags[ridx] = r.flags;
-        if (!(r.flags & PHOS_SHADOW)) {
-          P.rays.mesh[ridx] = r.mesh;
-          P.rays.face[ridx] = r.face;
-          P.rays.u[ridx] = r.u;
-          P.rays.v[ridx] = r.v;
-        }
-      }
-      has_ray = false;
-    }
-    // 2. refill idle lanes from the warp's chunk
-    unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
-    if (__popc(idle) >= kRefillMin && (taken < cur_cnt || nxt_cnt != 0)) {
-      while (idle) {
-        if (taken == cur_cnt && !advance()) break;
-        const uint32_t rank = __popc(idle & lt_mask);
-        const uint32_t take = min((uint32_t)__popc(idle), cur_cnt - taken);
-        if (!has_ray && rank < take) {
-          const uint32_t k = taken + rank;
-          const uint32_t fl = stage[cur_buf][7][k];
-          if (!(fl & PHOS_MASKED)) {  // MASKED rays are consumed without being traced
-            r.ox = __uint_as_float(stage[cur_buf][0][k]);
-            r.oy = __uint_as_float(stage[cur_buf][1][k]);
-            r.oz = __uint_as_float(stage[cur_buf][2][k]);
-            r.wx = __uint_as_float(stage[cur_buf][3][k]);
-            r.wy = __uint_as_float(stage[cur_buf][4][k]);
-            r.wz = __uint_as_float(stage[cur_buf][5][k]);
-            r.d = __uint_as_float(stage[cur_buf][6][k]);
-            r.flags = fl;
-            r.order = 0xffffffffu;
-            r.mesh = r.face = 0u;
-            r.u = r.v = 0.0f;
-            rd = make_raydir(r.wx, r.wy, r.wz);
-            ridx = cur_base + k;
-            cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
-            st.sp = 0;
-            trem = lmask = 0u;
-            changed = false;
-            has_ray = true;
+    // 1. what every lane wants to do next (two ballots drive everything else)
+    const bool tri_work = has_ray && (trem | lmask) != 0u;
+    const bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || st.sp != 0);
+    const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
+    const unsigned nl = __ballot_sync(0xffffffffu, node_work);
+    // 2. enough lanes without work (finished rays or empty lanes): retire and refill from the chunk
+    if (__popc(~(tl | nl)) >= kRefillMin) {
+      if (has_ray && !tri_work && !node_work) {
+        if (changed) {
+          P.rays.d[ridx] = r.d;
+          P.rays.flags[ridx] = r.flags;
+          if (!(r.flags & PHOS_SHADOW)) {
+            P.rays.mesh[ridx] = r.mesh;
+            P.rays.face[ridx] = r.face;
+            P.rays.u[ridx] = r.u;
+            P.rays.v[ridx] = r.v;
           }
         }
-        taken += take;
-        idle = __ballot_sync(0xffffffffu, !has_ray);
+        has_ray = false;
       }
+      if (taken < cur_cnt || nxt_cnt != 0) {
+        unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+        while (idle) {
+          if (taken == cur_cnt && !advance()) break;
+          const uint32_t rank = __popc(idle & lt_mask);
+          const uint32_t take = min((uint32_t)__popc(idle), cur_cnt - taken);
+          if (!has_ray && rank < take) {
+            const uint32_t k = taken + rank;
+            const uint32_t fl = stage[cur_buf][7][k];
+            if (!(fl & PHOS_MASKED)) {  // MASKED rays are consumed without being traced
+              r.ox = __uint_as_float(stage[cur_buf][0][k]);
+              r.oy = __uint_as_float(stage[cur_buf][1][k]);
+              r.oz = __uint_as_float(stage[cur_buf][2][k]);
+              r.wx = __uint_as_float(stage[cur_buf][3][k]);
+              r.wy = __uint_as_float(stage[cur_buf][4][k]);
+              r.wz = __uint_as_float(stage[cur_buf][5][k]);
+              r.d = __uint_as_float(stage[cur_buf][6][k]);
+              r.flags = fl;
+              r.order = 0xffffffffu;
+              r.mesh = r.face = 0u;
+              r.u = r.v = 0.0f;
+              rd = make_raydir(r.wx, r.wy, r.wz);
+              ridx = cur_base + k;
+              cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
+              st.sp = 0;
+              trem = lmask = 0u;
+              changed = false;
+              has_ray = true;
+            }
+          }
+          taken += take;
+          idle = __ballot_sync(0xffffffffu, !has_ray);
+        }
+        continue;  // new rays: vote again
+      }
+      if ((tl | nl) == 0u) break;  // stream drained and every lane retired
     }
     // 3. vote: node step or triangle step
-    const unsigned act = __ballot_sync(0xffffffffu, has_ray);
-    if (act == 0u) break;  // stream drained and every lane retired
-    const bool tri_work = has_ray && (trem | lmask) != 0u;
-    const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
     // a triangle step is cheaper than a node step: PHOS_TRI_BIAS weights the vote
-    if (PHOS_TRI_BIAS * __popc(tl) >= __popc(act & ~tl)) {
+    if (PHOS_TRI_BIAS * __popc(tl) >= __popc(nl)) {
       if (tri_work) {
         if (trem == 0u) {  // open the next hit leaf, nearest octant first
           const uint32_t slot = (__ffs(lmask) - 1) ^ rd.oct;
@@ -228,22 +235,45 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
         if (trem) {
           const uint4* tp = P.accel.tris + 3ull * tptr;
           const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+#if PHOS_TRI_PAIR
+          // two triangles of the leaf per step: both 48-byte fetches are in flight together
+          const bool two = trem >= 2u;
+          uint4 a2 = a, b2 = b, c2 = c;
+          if (two) {
+            a2 = __ldg(tp + 3);
+            b2 = __ldg(tp + 4);
+            c2 = __ldg(tp + 5);
+          }
+          tptr += two ? 2u : 1u;
+          trem -= two ? 2u : 1u;
+          if (kCount) n_tris += two ? 2u : 1u;
+#else
+          const bool two = false;
+          const uint4 a2 = a, b2 = b, c2 = c;
           ++tptr;
           --trem;
           if (kCount) ++n_tris;
+#endif
           float ds, us, vs;
+          bool done = false;
           if (mt_triangle(a, b, c, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) && accept_hit(r, ds, us, vs, c)) {
             changed = true;
-            if (r.flags & PHOS_SHADOW) {  // any-hit: this ray is done
-              trem = lmask = 0u;
-              cur.y = 0u;
-              st.sp = 0;
-            }
+            done = (r.flags & PHOS_SHADOW) != 0u;
+          }
+          if (two && !done && mt_triangle(a2, b2, c2, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) &&
+              accept_hit(r, ds, us, vs, c2)) {
+            changed = true;
+            done = (r.flags & PHOS_SHADOW) != 0u;
+          }
+          if (done) {  // any-hit: this ray is finished
+            trem = lmask = 0u;
+            cur.y = 0u;
+            st.sp = 0;
           }
         }
       }
-    } else if (has_ray && !tri_work) {
-      if ((cur.y >> 8) == 0u && st.sp != 0) cur = st.pop();
+    } else if (node_work) {
+      if ((cur.y >> 8) == 0u) cur = st.pop();
       if (cur.y >> 8) {
         const uint32_t node = take_child(cur, rd.oct);
         if (cur.y >> 8) st.push(cur);

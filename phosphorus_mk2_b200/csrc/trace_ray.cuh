@@ -27,7 +27,10 @@ struct DevAccel {
 };
 
 constexpr int kTraceBlock = 128;  // threads per CTA
-constexpr int kSmemStack = 16;    // traversal-stack entries per ray held in shared memory
+#ifndef PHOS_SMEM_STACK
+#define PHOS_SMEM_STACK 12
+#endif
+constexpr int kSmemStack = PHOS_SMEM_STACK;  // traversal-stack entries per ray held in shared memory
 constexpr int kSpillStack = 80;   // further entries (local memory; only touched when the stack runs deeper)
 
 // relative slack of the slab test: covers the fp32 error of the fma plane formulation for rays far

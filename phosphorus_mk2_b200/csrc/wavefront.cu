@@ -419,6 +419,90 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   return cuda_ok(ctx, cudaGetLastError(), "render launch") ? PHOS_OK : PHOS_ERR_CUDA;
 }
 
+// The ray streams of BASELINE config 3, produced by the pipeline itself: run ONE bounce of sample
+// `sample` over the tiles and hand back either the next-event shadow-ray stream (which = 1: one query per
+// primary slot, SHADOW or SHADOW|MASKED, tmax = distance to the sampled light point) or the BSDF-sampled
+// bounce-ray stream (which = 0: cosine-sampled diffuse / GGX rays from the primary hits, compacted).
+int phos_cuda_wavefront_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, uint32_t sample, uint32_t spp_total,
+                             uint64_t seed64, int which, const phos_rays* out, uint64_t capacity, uint64_t* out_count) {
+  if (!ctx || !tiles || !out || !out_count) return PHOS_ERR_INVALID;
+  if (!ctx->render || !ctx->render->film || !ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "wavefront_rays before upload_scene / upload_accel");
+  if (sample >= spp_total) return fail(ctx, PHOS_ERR_INVALID, "bad sample index");
+  cudaSetDevice(ctx->device);
+  RenderState& R = *ctx->render;
+  const uint32_t seed = (uint32_t)(seed64 ^ (seed64 >> 32));
+  std::vector<unsigned long long> offsets(n_tiles);
+  unsigned long long total = 0;
+  uint32_t max_px = 0;
+  for (uint32_t i = 0; i < n_tiles; ++i) {
+    if (tiles[i].x + tiles[i].w > R.camera.width || tiles[i].y + tiles[i].h > R.camera.height)
+      return fail(ctx, PHOS_ERR_INVALID, "tile outside the film");
+    offsets[i] = total;
+    total += (unsigned long long)tiles[i].w * tiles[i].h;
+    max_px = std::max(max_px, tiles[i].w * tiles[i].h);
+  }
+  if (total == 0 || total > 0x7fffffffull || n_tiles > 65535) return fail(ctx, PHOS_ERR_INVALID, "bad tile list");
+  const uint32_t P = (uint32_t)total;
+  if (capacity < P) return fail(ctx, PHOS_ERR_INVALID, "output stream too small");
+  if (!R.ensure_wavefront(ctx, P, P) || !R.set_tiles(ctx, tiles, offsets.data(), n_tiles)) return PHOS_ERR_CUDA;
+  Wavefront& W = R.wf;
+  cudaStream_t st = ctx->stream;
+  pixel_table_kernel<<<dim3((max_px + 255) / 256, n_tiles), 256, 0, st>>>(R.d_tiles, R.d_tile_offsets, R.camera.width, W.pixel);
+  std::vector<float> jit;
+  film_jitter(seed, spp_total, jit);
+  if (R.jitter_capacity < spp_total) {
+    cudaStreamSynchronize(st);
+    if (R.d_jitter) cudaFree(R.d_jitter);
+    R.d_jitter = nullptr;
+    if (!cuda_ok(ctx, cudaMalloc(&R.d_jitter, 2 * sizeof(float) * spp_total), "cudaMalloc(jitter)")) return PHOS_ERR_CUDA;
+    R.jitter_capacity = spp_total;
+  }
+  if (!cuda_ok(ctx, cudaMemcpyAsync(R.d_jitter, jit.data(), 2 * sizeof(float) * spp_total, cudaMemcpyHostToDevice, st), "upload jitter"))
+    return PHOS_ERR_CUDA;
+  cudaStreamSynchronize(st);
+  FrameArgs A;
+  A.cam = R.camera;
+  A.scene = R.scene;
+  A.P = P;
+  A.Q = P;
+  A.spp_begin = sample;
+  A.seed = seed;
+  A.max_depth = std::max<uint32_t>(2, ctx->opt.path_depth);  // the first bounce must be allowed to continue
+  A.scale = 0.0f;
+  A.jitter = R.d_jitter;
+  A.pixel = W.pixel;
+  A.beta = W.beta;
+  A.rad = W.rad;
+  A.depth = W.depth;
+  A.n = W.n;
+  A.light_pdf = W.light_pdf;
+  A.count = W.count;
+  const uint32_t blocks = (P + 255) / 256;
+  paths_init_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.slot_path[0]);
+  int rc = launch_trace(ctx, W.rays[0], P, st, ctx->d_counters + 24, false, W.count);
+  if (rc) return rc;
+  shade_nee_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.slot_path[0], 0, W.shadow);
+  const phos_rays* src = &W.shadow;
+  uint32_t n = P;
+  if (which == 0) {
+    rc = launch_trace(ctx, W.shadow, P, st, ctx->d_counters + 25, false, W.count);
+    if (rc) return rc;
+    integrate_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.shadow, W.slot_path[0], 0, W.rays[1], W.slot_path[1]);
+    if (!cuda_ok(ctx, cudaMemcpyAsync(&n, W.count + 1, 4, cudaMemcpyDeviceToHost, st), "read queue length") ||
+        !cuda_ok(ctx, cudaStreamSynchronize(st), "wavefront_rays"))
+      return PHOS_ERR_CUDA;
+    src = &W.rays[1];
+  }
+  ctx->launches += 5;
+  const void* sp[12] = {src->px, src->py, src->pz, src->wx, src->wy, src->wz, src->d, src->mesh, src->face, src->u, src->v, src->flags};
+  void* dp[12] = {out->px, out->py, out->pz, out->wx, out->wy, out->wz, out->d, out->mesh, out->face, out->u, out->v, out->flags};
+  for (int k = 0; k < 12; ++k)
+    if (n && !cuda_ok(ctx, cudaMemcpyAsync(dp[k], sp[k], (size_t)n * 4, cudaMemcpyDeviceToDevice, st), "copy stream")) return PHOS_ERR_CUDA;
+  if (!cuda_ok(ctx, cudaStreamSynchronize(st), "wavefront_rays")) return PHOS_ERR_CUDA;
+  *out_count = n;
+  return PHOS_OK;
+}
+
 int phos_cuda_film_clear(phos_ctx* ctx) {
   if (!ctx || !ctx->render || !ctx->render->film) return PHOS_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -170,6 +170,11 @@ class CudaDevice:
     def trace_device(self, rays: DeviceRays) -> None:
         self._check(self._L.phos_cuda_trace_device(self._ctx, C.byref(rays.s), rays.n))
 
+    def trace_device_n(self, rays: DeviceRays, n: int) -> None:
+        """Trace the first n rays of a device stream."""
+        assert n <= rays.n
+        self._check(self._L.phos_cuda_trace_device(self._ctx, C.byref(rays.s), n))
+
     def trace_count(self, rays: DeviceRays) -> tuple[int, int]:
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._check(self._L.phos_cuda_trace_count(self._ctx, C.byref(rays.s), rays.n, C.byref(a), C.byref(b)))
@@ -191,6 +196,16 @@ class CudaDevice:
         [spp_begin, spp_end) of the tiles' pixels into the device film.  Asynchronous."""
         arr = tile_array(tiles)
         self._check(self._L.phos_cuda_render(self._ctx, arr, len(tiles), spp_begin, spp_end, spp_total, seed))
+
+    def wavefront_rays(self, tiles, rays: DeviceRays, which: str = "bounce", sample: int = 0, spp_total: int = 1,
+                       seed: int = 0) -> int:
+        """One bounce of the pipeline; `rays` receives the bounce-ray stream (compacted) or the
+        next-event shadow-ray stream.  Returns the number of rays written."""
+        arr = tile_array(tiles)
+        n = C.c_uint64(0)
+        self._check(self._L.phos_cuda_wavefront_rays(self._ctx, arr, len(tiles), sample, spp_total, seed,
+                                                     0 if which == "bounce" else 1, C.byref(rays.s), rays.n, C.byref(n)))
+        return int(n.value)
 
     def film_clear(self) -> None:
         self._check(self._L.phos_cuda_film_clear(self._ctx))

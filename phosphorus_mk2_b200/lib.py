@@ -74,6 +74,7 @@ SYMBOLS = {
     "phos_cuda_upload_scene": (_I, [_VP, C.POINTER(PhosSceneDesc)]),
     "phos_cuda_camera_rays": (_I, [_VP, C.POINTER(PhosTile), _U32, C.c_float, C.c_float, _RP]),
     "phos_cuda_render": (_I, [_VP, C.POINTER(PhosTile), _U32, _U32, _U32, _U32, _U64]),
+    "phos_cuda_wavefront_rays": (_I, [_VP, C.POINTER(PhosTile), _U32, _U32, _U32, _U64, _I, _RP, _U64, C.POINTER(_U64)]),
     "phos_cuda_film_clear": (_I, [_VP]),
     "phos_cuda_film_device_ptr": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U64)]),
     "phos_cuda_film_read": (_I, [_VP, _VP, _U32, _U32, _U32, _U32]),

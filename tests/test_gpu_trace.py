@@ -138,3 +138,27 @@ def test_config2_full_size_properties(device, oracle):
     sh = device.trace(sh)
     assert np.array_equal(sh.hit, hit)
     assert np.all(sh.mesh == 12345)
+
+
+def test_config3_ray_sets_against_oracle(device, oracle):
+    """BASELINE config 3's ray sets at reduced size (318 k-triangle terrain, 256 x 256): the incoherent
+    BSDF-sampled bounce rays and the next-event shadow rays produced by the pipeline itself, traced
+    through the C ABI and compared ray for ray with the oracle."""
+    from phosphorus_mk2_b200.device import make_tiles
+    sc = scenes.terrain(n=400, width=256, height=256)
+    acc = Accel(sc)
+    device.preprocess(sc, acc)
+    device.upload_scene(sc)
+    nodes, packets = acc.nodes_array(), acc.packets_array()
+    tiles = make_tiles(256, 256)
+    for which in ("bounce", "shadow"):
+        dr = device.device_rays(256 * 256)
+        n = device.wavefront_rays(tiles, dr, which, 0, 1, 42)
+        assert n > 1000
+        rays = dr.download().slice(0, n)
+        dr.free()
+        if which == "shadow":
+            assert np.all((rays.flags & SHADOW) != 0)
+        want, _ = oracle.traverse(nodes, packets, rays)
+        got = device.trace(rays.copy())
+        assert len(mismatches(rays, got, want)) == 0

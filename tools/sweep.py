@@ -30,7 +30,12 @@ def main():
             sc = scenes.terrain(n=a.terrain_n)
         acc = Accel(sc)
         host = None
-        if wl.endswith("_inc"):
+        wave = None
+        if wl.endswith("_bounce"):
+            wave = "bounce"  # BASELINE config 3, ray set A: BSDF-sampled bounce rays from the primary hits
+        elif wl.endswith("_nee"):
+            wave = "shadow"  # ray set B: next-event shadow rays
+        elif wl.endswith("_inc"):
             host = raysets.aimed_rays(sc, 1920 * 1080, seed=5)
         elif wl.endswith("_shadow"):
             host = raysets.as_shadow(raysets.aimed_rays(sc, 1920 * 1080, seed=5), seed=6, masked_fraction=0.0)
@@ -45,8 +50,17 @@ def main():
             dr = dev.device_rays(n)
             tiles = make_tiles(cam.film_width, cam.film_height)
 
+            nrays = n
+            if wave:
+                pristine = dev.device_rays(n)
+                nrays = dev.wavefront_rays(tiles, pristine, wave, 0, 1, 42)
+                host_w = pristine.download()
+                pristine.free()
+
             def fresh():
-                if host is None:
+                if wave:
+                    dr.upload(host_w)
+                elif host is None:
                     dev.camera_rays(tiles, dr)
                 else:
                     dr.upload(host)
@@ -55,18 +69,31 @@ def main():
                 dev.flush_l2()
                 fresh()
                 dev.timer_begin()
-                dev.trace_device(dr)
+                if wave:
+                    dev.trace_device_n(dr, nrays)
+                else:
+                    dev.trace_device(dr)
                 t = dev.timer_end()
                 if i >= 3:
                     ms.append(t)
             fresh()
-            nodes, tris = dev.trace_count(dr)
-            out = dr.download()
+            if wave:
+                sub = dev.device_rays(max(nrays, 1))
+                h2 = host_w.slice(0, max(nrays, 1))
+                sub.upload(h2)
+                nodes, tris = dev.trace_count(sub)
+                out = sub.download()
+                sub.free()
+                traced = int(((h2.flags & 2) == 0).sum())
+            else:
+                nodes, tris = dev.trace_count(dr)
+                out = dr.download()
+                traced = n
             sig = (int(out.flags.sum()), float(out.d[out.hit].astype(np.float64).sum()), int(out.face[out.hit].astype(np.uint64).sum()))
             if ref is None:
                 ref = sig
-            print(f"{wl:12s} {os.path.basename(lib):34s} {n/np.mean(ms)/1e3:9.1f} Mrays/s  min {n/np.min(ms)/1e3:9.1f}  "
-                  f"nodes/ray {nodes/n:.2f} tris/ray {tris/n:.2f} hit {out.hit.mean():.3f} same={sig == ref}", flush=True)
+            print(f"{wl:14s} {os.path.basename(lib):30s} {traced/np.mean(ms)/1e3:9.1f} Mrays/s  min {traced/np.min(ms)/1e3:9.1f}  "
+                  f"rays {traced} nodes/ray {nodes/max(traced,1):.2f} tris/ray {tris/max(traced,1):.2f} hit {out.hit.mean():.3f} same={sig == ref}", flush=True)
             dr.free()
             dev.close()
 
