@@ -133,6 +133,16 @@ class RefScene:
         secs = self.lib.ref_render(self.h, spp, pps, depth, 1 if single_threaded else 0, img.ctypes.data)
         return img, secs
 
+    def render_cuda(self, spp: int, pps: int = 1, depth: int = 9):
+        """The same frame through the drop-in GPU device: the reference's host code (scene_t, tiles_t,
+        sampler, film_t) driving cuda_t::preprocess/start/join (integration/cuda.cpp -> libphos_cuda.so)."""
+        cam = self._scene.camera
+        img = np.zeros((cam.film_height, cam.film_width, 4), np.float32)
+        secs = self.lib.ref_render_on(self.h, spp, pps, depth, 1, 1, img.ctypes.data)
+        if secs < 0:
+            raise RuntimeError("cuda_t raised (see stderr)")
+        return img, secs
+
     def num_lights(self):
         return self.lib.ref_scene_num_lights(self.h)
 
@@ -166,6 +176,9 @@ class RefLib:
         L.ref_trace.restype = C.c_double
         L.ref_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
         L.ref_render.restype = C.c_double
+        L.ref_render_on.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+        L.ref_render_on.restype = C.c_double
+        L.ref_cuda_device_count.restype = C.c_int
         L.ref_hardware_concurrency.restype = C.c_uint32
         L.ref_sizeof_node.restype = C.c_uint32
         L.ref_sizeof_packet.restype = C.c_uint32

@@ -113,3 +113,17 @@ bool material_t::is_emitter() const { return details->emitter(); }
 bool material_t::has_attribute(const std::string& name) const { return details->attributes.count(name); }
 void material_t::attach() {}
 void material_t::boot(const parsed_options_t&, const std::string&) {}
+
+// Which built-in closure is this material?  (Asked by the GPU device glue, integration/cuda.cpp; with the real
+// OSL material system the same answer comes from querying the shader group's layers and parameters.)
+bool material_builtin_closure(const material_t* m, uint32_t* kind, float cs[3], float* roughness, float* power) {
+  const auto* d = m->details;
+  if (d->node == "diffuse_emitter_node") *kind = 2;
+  else if (d->node == "glossy_bsdf_node") *kind = 1;
+  else if (d->node == "diffuse_bsdf_node") *kind = 0;
+  else return false;
+  cs[0] = d->cs.x; cs[1] = d->cs.y; cs[2] = d->cs.z;
+  *roughness = d->roughness;
+  *power = d->power;
+  return true;
+}

@@ -45,4 +45,12 @@ patch("accel/bvh/binned_sah_builder.hpp", "{ [0 ... 7] = { geometry } }",
       "{ geometry_t(geometry), geometry_t(geometry), geometry_t(geometry), geometry_t(geometry),"
       " geometry_t(geometry), geometry_t(geometry), geometry_t(geometry), geometry_t(geometry) }")
 patch("bsdf.hpp", "  template<>\n  inline void add_lobe(", "  inline void add_lobe(")
+# --- additive accessor for the GPU device glue (integration/cuda.cpp): the per-face
+# smooth flag lives in the private mesh_t::details_t (src/mesh.cpp:10-18)
+patch("mesh.hpp", "  inline bool has_per_vertex_normals() const {",
+      "  /* is this face shaded with interpolated vertex normals? (added for the GPU device) */\n"
+      "  bool is_smooth(uint32_t face) const;\n\n"
+      "  inline bool has_per_vertex_normals() const {")
+p = root / "mesh.cpp"
+p.write_text(p.read_text() + "\nbool mesh_t::is_smooth(uint32_t face) const {\n  return details->smooth[face];\n}\n")
 print("patched", root)

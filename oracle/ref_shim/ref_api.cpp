@@ -20,6 +20,7 @@
 #include "scene.hpp"
 #include "state.hpp"
 #include "xpu/cpu.hpp"
+#include "xpu/cuda.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -238,7 +239,15 @@ double ref_trace(void* h, int kind, float* const* f, uint32_t* const* u, uint64_
 
 // Render a frame with the reference's own CPU device (cpu_t::preprocess/start/join) into an RGBA
 // float image.  Wall clock around start -> join like src/core.cpp:158-177.  Returns seconds.
+double ref_render_on(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, int use_cuda, float* rgba);
 double ref_render(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, float* rgba) {
+  return ref_render_on(h, spp, pps, depth, single_threaded, 0, rgba);
+}
+
+// The same frame through ANY xpu_t: use_cuda = 1 drives the drop-in GPU device (integration/cuda.cpp -> libphos_cuda.so)
+// with exactly the calls session_t::details_t::render makes (plugins/blender/session.cpp:73-94).
+// Returns seconds, or -1 with a message on stderr if the device raised.
+double ref_render_on(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, int use_cuda, float* rgba) {
   auto* s = static_cast<ref_scene*>(h);
   parsed_options_t options;
   options.samples_per_pixel = spp;
@@ -251,8 +260,15 @@ double ref_render(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int singl
   render_buffer_t::descriptor_t format;
   format.request(render_buffer_t::PRIMARY, 4);
 
-  cpu_t* device = cpu_t::make(options);
-  device->preprocess(s->scene);
+  xpu_t* device = nullptr;
+  try {
+    device = use_cuda ? static_cast<xpu_t*>(cuda_t::make(options, 0)) : static_cast<xpu_t*>(cpu_t::make(options));
+    device->preprocess(s->scene);
+  } catch (const std::exception& e) {
+    std::cerr << "ref_render_on: " << e.what() << std::endl;
+    delete device;
+    return -1.0;
+  }
 
   job::tiles_t* tiles = job::tiles_t::make(W, H, 32, format);
   memory_film_t film;
@@ -273,6 +289,8 @@ double ref_render(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int singl
   // sampler_t::~sampler_t deletes posix_memalign'd memory (src/sampling.cpp:83-87); leak it instead.
   return dt;
 }
+
+int ref_cuda_device_count(void) { return cuda_t::device_count(); }
 
 uint32_t ref_hardware_concurrency(void) { return std::thread::hardware_concurrency(); }
 

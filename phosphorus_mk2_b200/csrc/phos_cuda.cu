@@ -66,6 +66,7 @@ static void* out_ptr(const phos_rays& r, int k) {
 int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t stream, unsigned long long* cursor,
                  bool count, const uint32_t* n_ptr) {
   if (n == 0) return PHOS_OK;
+  if (n >= (1ull << 32)) return fail(ctx, PHOS_ERR_INVALID, "more than 2^32 - 1 rays in one device stream");
   TraceArgs a;
   a.rays = dev;
   a.n = n;

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   // ---- the warp's view of the stream (all warp-uniform) ---------------------------------------------
   uint32_t phase = 0;  // bit b: parity the next wait on buffer b expects
   int cur_buf = 0;
-  unsigned long long cur_base = 0, nxt_base = 0;
+  uint32_t cur_base = 0, nxt_base = 0;  // ray indices fit 32 bits: launch_trace splits longer streams
   uint32_t cur_cnt = 0, taken = 0, nxt_cnt = 0;
   bool nxt_tma = false, exhausted = false;
 
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
       exhausted = true;
       return;
     }
-    nxt_base = base;
+    nxt_base = (uint32_t)base;
     nxt_cnt = (uint32_t)min((unsigned long long)kChunk, N - base);
     nxt_tma = P.tma_ok && nxt_cnt == kChunk;
     if (nxt_tma) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   RayDir rd;
   r.flags = 0;
   rd.oct = 0;
-  unsigned long long ridx = 0;
+  uint32_t ridx = 0;
   bool has_ray = false, changed = false;
   uint2 cur = make_uint2(0u, 0u);
   uint32_t trem = 0, tptr = 0, lmask = 0, lcounts = 0, lbase = 0;
