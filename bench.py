@@ -401,7 +401,13 @@ def main():
         peak, peak_src = peaks()
         ms_kernel = total_ms / args.steps
         achieved = n * b_ray / (ms_kernel * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        traffic = None  # DRAM bytes per launch from the committed ncu capture of this workload, if there is one
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": n * b_ray,
                 "kernel": "trace_kernel", "peak_source": peak_src, "bytes_per_ray": b_ray,
                 "oracle_nodes_per_ray": n_node, "oracle_tris_per_ray": n_tri,
                 "gpu_fetched_bytes_per_ray": B_IO_CLOSEST + (g_nodes * S_NODE + g_tris * S_TRI) / n,

@@ -9,8 +9,9 @@
 
 namespace phos {
 
-constexpr int kPipe = 3;                     // host-pointer trace: chunks in flight
-constexpr uint64_t kPipeChunk = 1ull << 20;  // rays per chunk (48 MiB in, 24 MiB out)
+constexpr int kPipe = 4;                     // host-pointer trace: chunks in flight
+constexpr uint64_t kPipeChunk = 1ull << 18;  // rays per chunk (12 MiB in, 6 MiB out): small enough that the
+                                             // up- and down-link of PCIe are both busy most of the call
 
 struct PipeLane {
   cudaStream_t stream = nullptr;

@@ -240,7 +240,7 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
   if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "trace before upload_accel");
   if (n == 0) return PHOS_OK;
   cudaSetDevice(ctx->device);
-  const uint64_t chunk = std::min<uint64_t>(kPipeChunk, std::max<uint64_t>(32768, (n + kPipe - 1) / kPipe));
+  const uint64_t chunk = std::min<uint64_t>(kPipeChunk, std::max<uint64_t>(32768, (n + 2 * kPipe - 1) / (2 * kPipe)));
   for (int i = 0; i < kPipe; ++i) {
     if (ctx->pipe[i].capacity < chunk) {
       cudaStreamSynchronize(ctx->pipe[i].stream);
