@@ -205,3 +205,16 @@ def terrain(n: int = 2237, extent: float = 100.0, seed: int = 1234, width: int =
 def heightfield(g: int, seed: int = 7) -> Scene:
     """Small g x g x 2 triangle heightfield used by parity tests (the survey's probe mesh family)."""
     return terrain(n=g + 1, extent=10.0, seed=seed, width=256, height=256)
+
+
+def instanced_field(grid: int = 86, width: int = 3840, height: int = 2160) -> Scene:
+    """Config 5: ~30 M triangles as world-space-baked copies of one 4096-triangle object (the reference
+    has no instancing: every copy is its own mesh_t), lit by one large emissive quad above the field.
+    grid = 86 -> 7396 copies = 30 294 016 triangles (+ 2 for the light)."""
+    s = sphere_field(grid=grid, width=width, height=height)
+    light = s.add_material(Material(MAT_EMITTER, (1.0, 0.95, 0.9), power=60.0))
+    e = 0.5 * grid
+    v, f = [], []
+    _quad(v, f, (-e, 0.45 * grid, -e), (e, 0.45 * grid, -e), (e, 0.45 * grid, e), (-e, 0.45 * grid, e), (0, -1, 0))
+    s.add(Mesh(np.array(v), np.array(f), [(light, np.arange(2))]))
+    return s

@@ -162,3 +162,93 @@ def test_config3_ray_sets_against_oracle(device, oracle):
         want, _ = oracle.traverse(nodes, packets, rays)
         got = device.trace(rays.copy())
         assert len(mismatches(rays, got, want)) == 0
+
+
+def test_config3_full_size_properties(device, oracle):
+    """BASELINE config 3 at full size: 9 999 394-triangle displaced terrain (+ sky quad), the bounce-ray
+    and shadow-ray streams of a 1920 x 1080 frame.  A 20 000-ray sample of each stream is compared
+    ray for ray with the oracle traversal of the same 10 M-triangle tree; the whole streams are checked
+    through size-independent properties."""
+    from phosphorus_mk2_b200.device import make_tiles
+    sc = scenes.terrain()
+    assert sc.num_triangles() == 9_999_394
+    acc = Accel(sc)
+    device.preprocess(sc, acc)
+    device.upload_scene(sc)
+    st = device.accel_stats()
+    assert st.triangles == 9_999_394 and st.max_depth + 2 <= 12  # the re-grouped tree fits the shared-memory stack
+    nodes, packets = acc.nodes_array(), acc.packets_array()
+    tiles = make_tiles(1920, 1080)
+    rng = np.random.default_rng(3)
+    F = ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags")
+    for which in ("bounce", "shadow"):
+        dr = device.device_rays(1920 * 1080)
+        n = device.wavefront_rays(tiles, dr, which, 0, 1, 42)
+        rays = dr.download().slice(0, n)
+        assert n > 1_500_000
+        device.trace_device_n(dr, n)
+        got = dr.download().slice(0, n)
+        dr.free()
+        idx = np.sort(rng.choice(n, 20000, replace=False))
+        sample, sub = RayBatch(len(idx)), RayBatch(len(idx))
+        for f in F:
+            getattr(sample, f)[:] = getattr(rays, f)[idx]
+            getattr(sub, f)[:] = getattr(got, f)[idx]
+        want, _ = oracle.traverse(nodes, packets, sample)
+        assert len(mismatches(sample, sub, want)) == 0, which
+        if which == "bounce":
+            hit = got.hit
+            assert 0.2 < hit.mean() < 0.9
+            # idempotence: with tmax = the reported distance nothing closer exists
+            again = rays.copy()
+            again.d[:] = got.d
+            again = device.trace(again)
+            assert np.all(again.d[hit] == got.d[hit]) and not np.any(again.hit[~hit])
+            assert np.all(got.u[hit] >= 0) and np.all(got.v[hit] >= 0) and np.all(got.u[hit] + got.v[hit] <= 1 + 1e-6)
+        else:
+            masked = (rays.flags & MASKED) != 0
+            assert np.array_equal(got.mesh, rays.mesh) and np.array_equal(got.face, rays.face)  # light ids untouched
+            assert not np.any(got.hit[masked])                                                   # never traced
+            assert np.all(got.d[got.hit] < rays.d[got.hit])
+
+
+def test_ragged_and_degenerate_streams(device, oracle):
+    """Edge cases: stream lengths around the 32-ray chunk and the 128-thread CTA, a misaligned device
+    view (no TMA), all-masked and all-miss streams, zero-length and NaN-free degenerate directions."""
+    sc = scenes.heightfield(40)
+    acc = Accel(sc)
+    device.preprocess(sc, acc)
+    nodes, packets = acc.nodes_array(), acc.packets_array()
+    base = raysets.aimed_rays(sc, 700, seed=77)
+    for n in (2, 32, 63, 64, 65, 127, 129, 511, 700):
+        rays = base.slice(0, n)
+        want, _ = oracle.traverse(nodes, packets, rays)
+        assert len(mismatches(rays, device.trace(rays.copy()), want)) == 0, n
+    # misaligned host views (odd element offsets): the host path stages them, results identical
+    off = RayBatch(699)
+    for f in ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags"):
+        setattr(off, f, getattr(base, f)[1:])
+    want, _ = oracle.traverse(nodes, packets, base.slice(1, 700))
+    cp = RayBatch(699)
+    for f in ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags"):
+        getattr(cp, f)[:] = getattr(off, f)
+    assert len(mismatches(base.slice(1, 700), device.trace(cp), want)) == 0
+    # all masked: nothing is touched
+    m = base.copy()
+    m.flags[:] = MASKED | SHADOW
+    out = device.trace(m.copy())
+    for f in ("d", "u", "v", "mesh", "face", "flags"):
+        assert np.array_equal(bits(getattr(out, f)), bits(getattr(m, f)))
+    # all miss: rays leaving the scene
+    away = base.copy()
+    away.wy[:] = np.abs(away.wy) + 1.0
+    away.py[:] = 100.0
+    out = device.trace(away.copy())
+    assert not out.hit.any() and np.array_equal(bits(out.d), bits(away.d))
+    # zero direction components and tmax = 0
+    z = base.slice(0, 64)
+    z.wx[:32] = 0.0
+    z.wz[32:] = -0.0
+    z.d[::7] = 0.0
+    want, _ = oracle.traverse(nodes, packets, z)
+    assert len(mismatches(z, device.trace(z.copy()), want)) == 0
