@@ -1,19 +1,22 @@
 // trace.cuh — the ray-query kernel (sm_100a): persistent warps that drain a ray stream through the
 // node / triangle steps of trace_ray.cuh.
 //
-//   * work distribution: every warp claims 64-ray chunks of the stream from one global cursor; the
+//   * work distribution: every warp claims 32-ray chunks of the stream from one global cursor; the
 //     chunk's eight input arrays (p, wi, d, flags) are staged into shared memory with TMA bulk copies
 //     (cp.async.bulk + mbarrier), double-buffered so the next chunk lands while the current one is
 //     being traversed; a partial tail chunk (or a misaligned stream) is staged with plain loads;
-//   * per-lane refill: a lane whose ray is finished writes its hit record and takes the next ray of
-//     the warp's chunk as soon as enough lanes are idle (ballot + popc ranks, no atomics), so a long
-//     ray never holds 31 finished lanes hostage;
-//   * warp-voted phases: each iteration the warp either runs one node step (8 quantised child boxes)
-//     for the lanes that need one, or one Möller–Trumbore step for the lanes with pending leaf
-//     triangles — whichever more lanes want — so both inner loops run converged instead of every
-//     lane dragging the warp through its own leaf loop;
+//   * per-lane refill: a lane whose ray is finished keeps its result until enough lanes are without
+//     work, then all of them write their hit records and take the next rays of the warp's chunk
+//     (ballot + popc ranks, no atomics), so a long ray never holds 31 finished lanes hostage;
+//   * warp-voted phases: two ballots per iteration say what every lane wants next; the warp then runs
+//     either one node step (8 quantised child boxes, ~245 instructions) for the lanes that need one,
+//     or one Möller–Trumbore step (~60 instructions) for the lanes with pending leaf triangles — the
+//     vote is weighted towards the cheaper triangle step — so both inner loops run converged instead
+//     of every lane dragging the warp through its own leaf loop;
 //   * traversal stack: kSmemStack entries per ray in shared memory ([entry][thread], conflict-free),
 //     deeper entries in a local-memory spill that ordinary trees never touch.
+// Measured alternatives that did not pay off (profiles/r01_summary.md): L1 prefetch of the next node,
+// 64 registers / 8 CTAs per SM, sorting the ray stream, fused leaves.
 #pragma once
 #include "trace_ray.cuh"
 
@@ -34,9 +37,6 @@ namespace phos {
 #endif
 #ifndef PHOS_TRI_PAIR
 #define PHOS_TRI_PAIR 0
-#endif
-#ifndef PHOS_PREFETCH
-#define PHOS_PREFETCH 0
 #endif
 constexpr int kChunk = PHOS_CHUNK;           // rays per claimed chunk
 constexpr int kRefillMin = PHOS_REFILL_MIN;  // idle lanes that trigger a refill
@@ -283,19 +283,6 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
         lcounts = h.counts;
         lbase = h.tri_base;
         cur = make_uint2(h.child_base, h.imask | (h.inner << 8));
-#if PHOS_PREFETCH
-        if (h.inner) {  // the child this ray opens next: pull its 80 bytes towards L1 while other work runs
-          uint2 peek = cur;
-          const char* nn = (const char*)(P.accel.nodes + 5ull * take_child(peek, rd.oct));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(nn));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(nn + 64));
-        }
-        if (h.leaf) {
-          const uint32_t slot = (__ffs(h.leaf) - 1) ^ rd.oct;
-          const char* tt = (const char*)(P.accel.tris + 3ull * (h.tri_base + nibble_prefix(h.counts, slot)));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(tt));
-        }
-#endif
       }
     }
   }
