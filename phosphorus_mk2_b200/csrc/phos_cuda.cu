@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -127,8 +128,11 @@ phos_ctx* phos_cuda_create(int device, const phos_options* options) {
   if (options) ctx->opt = *options;
   else ctx->opt = phos_options{16, 16, 9};
   bool ok = cuda_ok(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  for (cudaStream_t* st : {&ctx->s_in, &ctx->s_cmp, &ctx->s_out})
+    ok = ok && cuda_ok(nullptr, cudaStreamCreateWithFlags(st, cudaStreamNonBlocking), "cudaStreamCreate");
   for (int i = 0; ok && i < kPipe; ++i)
-    ok = cuda_ok(nullptr, cudaStreamCreateWithFlags(&ctx->pipe[i].stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (cudaEvent_t* ev : {&ctx->pipe[i].ev_in, &ctx->pipe[i].ev_cmp, &ctx->pipe[i].ev_out})
+      ok = ok && cuda_ok(nullptr, cudaEventCreateWithFlags(ev, cudaEventDisableTiming), "cudaEventCreate");
   ok = ok && cuda_ok(nullptr, cudaEventCreate(&ctx->ev_begin), "cudaEventCreate") &&
        cuda_ok(nullptr, cudaEventCreate(&ctx->ev_end), "cudaEventCreate") &&
        cuda_ok(nullptr, cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long)), "cudaMalloc(counters)") &&
@@ -150,8 +154,11 @@ void phos_cuda_destroy(phos_ctx* ctx) {
   cudaDeviceSynchronize();
   for (int i = 0; i < kPipe; ++i) {
     free_rays(ctx->pipe[i].rays);
-    if (ctx->pipe[i].stream) cudaStreamDestroy(ctx->pipe[i].stream);
+    for (cudaEvent_t ev : {ctx->pipe[i].ev_in, ctx->pipe[i].ev_cmp, ctx->pipe[i].ev_out})
+      if (ev) cudaEventDestroy(ev);
   }
+  for (cudaStream_t st : {ctx->s_in, ctx->s_cmp, ctx->s_out})
+    if (st) cudaStreamDestroy(st);
   phos_render_release(ctx);
   if (ctx->d_nodes) cudaFree(ctx->d_nodes);
   if (ctx->d_tris) cudaFree(ctx->d_tris);
@@ -232,44 +239,74 @@ int phos_cuda_trace_count(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint
   return PHOS_OK;
 }
 
-// Host-pointer trace: the stream is cut into chunks that flow through kPipe lanes, each lane
-// (its own CUDA stream and device staging stream) doing H2D -> trace -> D2H, so the copies of one
-// chunk overlap the traversal of another.
+// Host-pointer trace: the stream is cut into chunks that flow through kPipe staging slots; all copies in
+// run on one stream, all traversals on a second, all copies out on a third, chained per slot by events,
+// so the up-link, the SMs and the down-link work on different chunks at the same time.
 int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
   if (!ctx || !rays) return PHOS_ERR_INVALID;
   if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "trace before upload_accel");
   if (n == 0) return PHOS_OK;
   cudaSetDevice(ctx->device);
-  const uint64_t chunk = std::min<uint64_t>(kPipeChunk, std::max<uint64_t>(32768, (n + 2 * kPipe - 1) / (2 * kPipe)));
+  uint64_t chunk = std::min<uint64_t>(kPipeChunk, std::max<uint64_t>(32768, (n + 2 * kPipe - 1) / (2 * kPipe)));
+  if (const char* e = std::getenv("PHOS_PIPE_CHUNK")) chunk = std::max<uint64_t>(1024, std::strtoull(e, nullptr, 10));  // tuning
   for (int i = 0; i < kPipe; ++i) {
+    ctx->pipe[i].used = false;
     if (ctx->pipe[i].capacity < chunk) {
-      cudaStreamSynchronize(ctx->pipe[i].stream);
+      cudaStreamSynchronize(ctx->s_out);
       free_rays(ctx->pipe[i].rays);
       ctx->pipe[i].capacity = 0;
       if (!alloc_rays(ctx, chunk, ctx->pipe[i].rays)) return PHOS_ERR_CUDA;
       ctx->pipe[i].capacity = chunk;
     }
   }
-  int lane = 0;
-  for (uint64_t base = 0; base < n; base += chunk, lane = (lane + 1) % kPipe) {
+  // A stream whose twelve arrays sit in one slab at a constant stride (px, py, pz, wx, wy, wz, d, mesh, face,
+  // u, v, flags — what phos_cuda_host_alloc-based callers and phos_cuda_rays_alloc produce) moves with ONE
+  // pitched copy per chunk and direction instead of 12 + 6: every copy call costs the host ~20 us here,
+  // as much as the wire time of a 1 MB array, so the call count, not PCIe, was the limit.
+  const char* slab[12] = {(const char*)rays->px, (const char*)rays->py, (const char*)rays->pz, (const char*)rays->wx,
+                          (const char*)rays->wy, (const char*)rays->wz, (const char*)rays->d,  (const char*)rays->mesh,
+                          (const char*)rays->face, (const char*)rays->u, (const char*)rays->v, (const char*)rays->flags};
+  const ptrdiff_t hstride = slab[1] - slab[0];
+  bool pitched = hstride >= (ptrdiff_t)(n * 4);
+  for (int k = 2; pitched && k < 12; ++k) pitched = slab[k] - slab[k - 1] == hstride;
+  int slot = 0;
+  bool ok = true;
+  for (uint64_t base = 0; ok && base < n; base += chunk, slot = (slot + 1) % kPipe) {
     const uint64_t cnt = std::min(chunk, n - base);
-    PipeLane& L = ctx->pipe[lane];
-    for (int k = 0; k < 12; ++k) {
+    PipeLane& L = ctx->pipe[slot];
+    const size_t dstride = (size_t)((const char*)L.rays.py - (const char*)L.rays.px);
+    if (L.used) ok = cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_in, L.ev_out, 0), "pipeline wait");  // slot free again
+    if (ok && pitched)
+      ok = cuda_ok(ctx, cudaMemcpy2DAsync(L.rays.px, dstride, slab[0] + base * 4, (size_t)hstride, cnt * 4, 12, cudaMemcpyHostToDevice, ctx->s_in),
+                   "H2D rays");
+    for (int k = 0; ok && !pitched && k < 12; ++k) {
       const char* src = (const char*)in_ptr(*rays, k) + base * 4;
-      if (!cuda_ok(ctx, cudaMemcpyAsync((void*)in_ptr(L.rays, k), src, cnt * 4, cudaMemcpyHostToDevice, L.stream), "H2D rays"))
-        return PHOS_ERR_CUDA;
+      ok = cuda_ok(ctx, cudaMemcpyAsync((void*)in_ptr(L.rays, k), src, cnt * 4, cudaMemcpyHostToDevice, ctx->s_in), "H2D rays");
     }
-    const int rc = launch_trace(ctx, L.rays, cnt, L.stream, ctx->d_counters + 16 + lane, false);
+    ok = ok && cuda_ok(ctx, cudaEventRecord(L.ev_in, ctx->s_in), "pipeline record") &&
+         cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_cmp, L.ev_in, 0), "pipeline wait");
+    if (!ok) break;
+    const int rc = launch_trace(ctx, L.rays, cnt, ctx->s_cmp, ctx->d_counters + 16 + slot, false);
     if (rc) return rc;
-    for (int k = 0; k < 6; ++k) {
+    ok = cuda_ok(ctx, cudaEventRecord(L.ev_cmp, ctx->s_cmp), "pipeline record") &&
+         cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_out, L.ev_cmp, 0), "pipeline wait");
+    if (ok && pitched)  // rows 6..11 of the slab: d, mesh, face, u, v, flags
+      ok = cuda_ok(ctx, cudaMemcpy2DAsync((void*)(slab[6] + base * 4), (size_t)hstride, L.rays.d, dstride, cnt * 4, 6, cudaMemcpyDeviceToHost, ctx->s_out),
+                   "D2H rays");
+    for (int k = 0; ok && !pitched && k < 6; ++k) {
       char* dst = (char*)out_ptr(*rays, k) + base * 4;
-      if (!cuda_ok(ctx, cudaMemcpyAsync(dst, out_ptr(L.rays, k), cnt * 4, cudaMemcpyDeviceToHost, L.stream), "D2H rays"))
-        return PHOS_ERR_CUDA;
+      ok = cuda_ok(ctx, cudaMemcpyAsync(dst, out_ptr(L.rays, k), cnt * 4, cudaMemcpyDeviceToHost, ctx->s_out), "D2H rays");
     }
+    ok = ok && cuda_ok(ctx, cudaEventRecord(L.ev_out, ctx->s_out), "pipeline record");
+    L.used = true;
   }
-  for (int i = 0; i < kPipe; ++i)
-    if (!cuda_ok(ctx, cudaStreamSynchronize(ctx->pipe[i].stream), "trace pipeline")) return PHOS_ERR_CUDA;
-  return PHOS_OK;
+  if (!ok) {
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->s_cmp);
+    cudaStreamSynchronize(ctx->s_out);
+    return PHOS_ERR_CUDA;
+  }
+  return cuda_ok(ctx, cudaStreamSynchronize(ctx->s_out), "trace pipeline") ? PHOS_OK : PHOS_ERR_CUDA;
 }
 
 int phos_cuda_rays_alloc(phos_ctx* ctx, uint64_t n, phos_rays* out) {

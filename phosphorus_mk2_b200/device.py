@@ -270,10 +270,11 @@ def pinned_ray_batch(n: int) -> RayBatch:
     if not base:
         raise PhosError("phos_cuda_host_alloc failed")
     r._pinned = base
-    names_f = ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v")
-    names_u = ("mesh", "face", "flags")
-    for i, k in enumerate(names_f + names_u):
-        ct = C.c_float if k in names_f else C.c_uint32
+    # one slab, constant stride, in the library's own array order: phos_cuda_trace then moves a chunk with a
+    # single pitched copy per direction (see csrc/phos_cuda.cu)
+    order = ("px", "py", "pz", "wx", "wy", "wz", "d", "mesh", "face", "u", "v", "flags")
+    for i, k in enumerate(order):
+        ct = C.c_uint32 if k in ("mesh", "face", "flags") else C.c_float
         arr = np.ctypeslib.as_array(C.cast(base + stride * i, C.POINTER(ct)), (n,))
         setattr(r, k, arr)
     return r
