@@ -21,6 +21,8 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline uint4 __ldg(const uint4* p) { return *p; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
   const uint64_t t = ((uint64_t)y << 32) | x;
   uint32_t r = 0;
