@@ -30,13 +30,13 @@ namespace phos {
 #define PHOS_REFILL_MIN 6
 #endif
 #ifndef PHOS_TRI_BIAS
-#define PHOS_TRI_BIAS 2
+#define PHOS_TRI_BIAS 3
 #endif
 #ifndef PHOS_MIN_BLOCKS
 #define PHOS_MIN_BLOCKS 7
 #endif
 #ifndef PHOS_TRI_PAIR
-#define PHOS_TRI_PAIR 0
+#define PHOS_TRI_PAIR 1
 #endif
 constexpr int kChunk = PHOS_CHUNK;           // rays per claimed chunk
 constexpr int kRefillMin = PHOS_REFILL_MIN;  // idle lanes that trigger a refill
@@ -151,9 +151,21 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   claim(1);
 
   // ---- per-lane traversal state ----------------------------------------------------------------------
-  Stack st;
-  st.smem = s_stack + threadIdx.x;
-  st.sp = 0;
+  // traversal stack: sp in a register, entries in this thread's shared-memory column (plain STS / LDS),
+  // deeper entries in a local array that ordinary trees never touch (the Stack struct of trace_ray.cuh
+  // is the same thing for the one-ray loop; taking it apart here keeps sp out of local memory)
+  uint2* const my_stack = s_stack + threadIdx.x;
+  uint2 spill[kSpillStack];
+  int sp = 0;
+  auto push = [&](uint2 v) {
+    if (sp < kSmemStack) my_stack[sp * kTraceBlock] = v;
+    else if (sp < kSmemStack + kSpillStack) spill[sp - kSmemStack] = v;
+    ++sp;
+  };
+  auto pop = [&]() -> uint2 {
+    --sp;
+    return sp < kSmemStack ? my_stack[sp * kTraceBlock] : spill[sp - kSmemStack];
+  };
   Ray r;
   RayDir rd;
   r.flags = 0;
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   for (;;) {
     // 1. what every lane wants to do next (two ballots drive everything else)
     const bool tri_work = has_ray && (trem | lmask) != 0u;
-    const bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || st.sp != 0);
+    const bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
     const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
     const unsigned nl = __ballot_sync(0xffffffffu, node_work);
     // 2. enough lanes without work (finished rays or empty lanes): retire and refill from the chunk
@@ -209,7 +221,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
               rd = make_raydir(r.wx, r.wy, r.wz);
               ridx = cur_base + k;
               cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
-              st.sp = 0;
+              sp = 0;
               trem = lmask = 0u;
               changed = false;
               has_ray = true;
@@ -268,15 +280,15 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
           if (done) {  // any-hit: this ray is finished
             trem = lmask = 0u;
             cur.y = 0u;
-            st.sp = 0;
+            sp = 0;
           }
         }
       }
     } else if (node_work) {
-      if ((cur.y >> 8) == 0u) cur = st.pop();
+      if ((cur.y >> 8) == 0u) cur = pop();
       if (cur.y >> 8) {
         const uint32_t node = take_child(cur, rd.oct);
-        if (cur.y >> 8) st.push(cur);
+        if (cur.y >> 8) push(cur);
         const NodeHits h = node_test(P.accel, node, r.ox, r.oy, r.oz, rd, r.d * PHOS_CULL_SLACK);
         if (kCount) ++n_nodes;
         lmask = h.leaf;

@@ -84,4 +84,28 @@ int emul_trace(const void* nodes288, uint32_t n_nodes, const void* packets384, u
   if (out_tris) *out_tris = tt;
   return 0;
 }
+
+// FNV-1a digest of the packed arrays (re-pack determinism across thread counts / knobs)
+int emul_repack_digest(const void* nodes288, uint32_t n_nodes, const void* packets384, uint32_t n_packets, uint64_t* digest,
+                       uint32_t* out_stats /*4*/) {
+  using namespace phos;
+  PackedAccel packed;
+  std::string e;
+  if (!repack_accel((const RefNode*)nodes288, n_nodes, (const RefPacket*)packets384, n_packets, packed, e)) return 1;
+  uint64_t h = 1469598103934665603ull;
+  auto eat = [&](const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  };
+  eat(packed.nodes.data(), packed.nodes.size() * sizeof(GNode));
+  eat(packed.tris.data(), packed.tris.size() * sizeof(GTri));
+  *digest = h;
+  if (out_stats) {
+    out_stats[0] = (uint32_t)packed.nodes.size();
+    out_stats[1] = (uint32_t)packed.tris.size();
+    out_stats[2] = packed.max_depth;
+    out_stats[3] = packed.max_leaf_tris;
+  }
+  return 0;
+}
 }

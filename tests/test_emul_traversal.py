@@ -46,6 +46,41 @@ def test_emulated_traversal_larger_scene_against_oracle(emul, oracle):
         assert stats[2] + 2 <= 24  # fits the shared-memory stack
 
 
+def _digest(emul, nodes, packets):
+    d = C.c_uint64()
+    stats = (C.c_uint32 * 4)()
+    assert emul.emul_repack_digest(nodes.ctypes.data, len(nodes) // 288, packets.ctypes.data, len(packets) // 384, C.byref(d), stats) == 0
+    return d.value, list(stats)
+
+
+def test_repack_is_independent_of_the_thread_count(emul, monkeypatch):
+    """The re-pack runs a level's nodes on all host threads and bins big ranges in parallel chunks; the
+    packed arrays must not depend on that (min / max / integer sums only)."""
+    sc = scenes.heightfield(300, seed=3)  # 180 k triangles: several chunks per split at the top
+    a = Accel(sc)
+    nodes, packets = a.nodes_array(), a.packets_array()
+    got = {}
+    for t in ("1", "3", "8"):
+        monkeypatch.setenv("PHOS_THREADS", t)
+        got[t] = _digest(emul, nodes, packets)
+    assert got["1"] == got["3"] == got["8"]
+    assert got["1"][1][1] == sc.num_triangles() and got["1"][1][3] <= 2
+
+
+@pytest.mark.parametrize("leaf", ["1", "2", "3", "15"])
+def test_leaf_size_knob_keeps_results(emul, oracle, monkeypatch, leaf):
+    """PHOS_REPACK_LEAF only changes how the reference leaves are cut; hits are the oracle's for any value."""
+    monkeypatch.setenv("PHOS_REPACK_LEAF", leaf)
+    sc = scenes.heightfield(120, seed=11)
+    a = Accel(sc)
+    nodes, packets = a.nodes_array(), a.packets_array()
+    for rays in (raysets.aimed_rays(sc, 8000, seed=41), raysets.as_shadow(raysets.aimed_rays(sc, 8000, seed=43), seed=44)):
+        want, _ = oracle.traverse(nodes, packets, rays)
+        got, _, _, stats = run_emul(emul, nodes, packets, rays)
+        assert len(mismatches(rays, got, want)) == 0
+        assert stats[3] <= int(leaf) and stats[1] == sc.num_triangles()
+
+
 def test_repack_splits_oversized_leaves(emul, oracle):
     """A pile of coincident-centroid triangles makes the SAH builder emit one big leaf (> 15
     triangles); the re-pack must split it into <= 15-triangle leaves without losing a triangle."""

@@ -13,9 +13,10 @@ from phosphorus_mk2_b200.device import Accel, CudaDevice, Options, make_tiles
 from phosphorus_mk2_b200.rays import HIT
 
 which = sys.argv[1] if len(sys.argv) > 1 else "terrain"
+lib_path = os.path.abspath(sys.argv[2]) if len(sys.argv) > 2 else None  # a tuning variant of the device library
 sc = scenes.terrain() if which == "terrain" else scenes.sphere_field()
 acc = Accel(sc); nodes, packets = acc.nodes_array(), acc.packets_array()
-dev = CudaDevice.make(Options(), 0); dev.preprocess(sc, acc); dev.upload_scene(sc)
+dev = CudaDevice(Options(), 0, lib_path=lib_path); dev.preprocess(sc, acc); dev.upload_scene(sc)
 orc = Oracle(); cam = sc.camera
 tiles = make_tiles(cam.film_width, cam.film_height); n = cam.film_width * cam.film_height
 for stream in ("primary", "bounce", "shadow"):
@@ -28,7 +29,7 @@ for stream in ("primary", "bounce", "shadow"):
     dev.trace_device_n(dr, k); got = dr.download().slice(0, k); dr.free()
     t0 = time.time(); want, cnt = orc.traverse(nodes, packets, rays); dt = time.time() - t0
     bad = mismatches(rays, got, want)
-    print(f"{which} {stream}: {k} rays, oracle {dt:.1f} s, mismatches {len(bad)} ({len(bad)/k:.2e})", flush=True)
+    print(f"{which} {os.path.basename(lib_path or 'libphos_cuda.so')} {stream}: {k} rays, oracle {dt:.1f} s, mismatches {len(bad)} ({len(bad)/k:.2e})", flush=True)
     for i in bad[:10]:
         gh, wh = bool(got.flags[i] & HIT), bool(want.flags[i] & HIT)
         rel = abs(float(got.d[i]) - float(want.d[i])) / max(abs(float(want.d[i])), 1e-30) if gh and wh else float("nan")

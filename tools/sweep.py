@@ -41,7 +41,13 @@ def main():
             host = raysets.as_shadow(raysets.aimed_rays(sc, 1920 * 1080, seed=5), seed=6, masked_fraction=0.0)
         print(f"# {wl}: {sc.num_triangles()} tris, build {acc.build_seconds:.1f}s, setup {time.time()-t0:.1f}s", flush=True)
         ref = None
-        for lib in a.libs:
+        for spec in a.libs:  # "lib.so" or "lib.so:ENV=val,ENV2=val" (re-pack knobs are read from the environment)
+            lib, _, envs = spec.partition(":")
+            saved = {}
+            for kv in filter(None, envs.split(",")):
+                k, _, v = kv.partition("=")
+                saved[k] = os.environ.get(k)
+                os.environ[k] = v
             dev = CudaDevice(Options(), 0, lib_path=os.path.abspath(lib))
             dev.preprocess(sc, acc)
             dev.upload_scene(sc)
@@ -92,7 +98,12 @@ def main():
             sig = (int(out.flags.sum()), float(out.d[out.hit].astype(np.float64).sum()), int(out.face[out.hit].astype(np.uint64).sum()))
             if ref is None:
                 ref = sig
-            print(f"{wl:14s} {os.path.basename(lib):30s} {traced/np.mean(ms)/1e3:9.1f} Mrays/s  min {traced/np.min(ms)/1e3:9.1f}  "
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+            print(f"{wl:14s} {os.path.basename(spec):30s} {traced/np.mean(ms)/1e3:9.1f} Mrays/s  min {traced/np.min(ms)/1e3:9.1f}  "
                   f"rays {traced} nodes/ray {nodes/max(traced,1):.2f} tris/ray {tris/max(traced,1):.2f} hit {out.hit.mean():.3f} same={sig == ref}", flush=True)
             dr.free()
             dev.close()
