@@ -12,8 +12,9 @@
 //   after a node's sub-trees, ceil(count/8) per leaf (:243-267, src/accel/bvh.cpp:58-78).
 // Triangles are numbered mesh -> face set -> face (src/scene.cpp:58-62, src/mesh.cpp:118-128).
 //
-// Not a translation: the tree is built by independent sub-tree tasks on a thread pool and stitched
-// with prefix offsets, which gives the same numbering as the reference's single-threaded recursion.
+// Not a translation: the top of the tree is expanded node by node, every range below 32 Ki primitives
+// is built as an independent task on all host threads, and the pieces are laid out with prefix
+// offsets — the same arrays as the reference's single-threaded recursion, bit for bit.
 // All arithmetic is fp32 with no contraction (compile with -ffp-contract=off) because SAH costs
 // decide the topology.
 #include <algorithm>
@@ -31,6 +32,7 @@
 #include <vector>
 
 #include "../../include/phos_cuda.h"
+#include "host_parallel.hpp"
 #include "phos_internal.hpp"
 
 namespace phos {
@@ -87,13 +89,33 @@ struct Range {
   uint32_t count() const { return end - begin; }
 };
 
+// Ranges beyond this many primitives are scanned in parallel chunks.  Every scan of the build reduces
+// with min / max and integer counts only, so chunking cannot change a single bit of the result.
+constexpr size_t kScanGrain = 1u << 16;
+int g_scan_threads = 1;  // set by phos_bvh_build for the duration of one build
+
 Range make_range(const std::vector<Prim>& prims, uint32_t begin, uint32_t end) {
   Range r;
   r.begin = begin;
   r.end = end;
-  for (uint32_t i = begin; i < end; ++i) {
-    r.bounds.grow(prims[i].bounds);
-    r.centroid_bounds.grow(prims[i].centroid);
+  const size_t n = end - begin;
+  if (n <= 2 * kScanGrain || g_scan_threads <= 1) {
+    for (uint32_t i = begin; i < end; ++i) {
+      r.bounds.grow(prims[i].bounds);
+      r.centroid_bounds.grow(prims[i].centroid);
+    }
+    return r;
+  }
+  std::vector<Range> part((n + kScanGrain - 1) / kScanGrain);
+  parallel_chunks(n, kScanGrain, g_scan_threads, [&](size_t b, size_t e, size_t c) {
+    for (size_t i = begin + b; i < begin + e; ++i) {
+      part[c].bounds.grow(prims[i].bounds);
+      part[c].centroid_bounds.grow(prims[i].centroid);
+    }
+  });
+  for (const Range& q : part) {
+    r.bounds.grow(q.bounds);
+    r.centroid_bounds.grow(q.centroid_bounds);
   }
   return r;
 }
@@ -118,10 +140,30 @@ Split find_split(const std::vector<Prim>& prims, const Range& g) {
     if (g.centroid_bounds.hi[axis] < g.centroid_bounds.lo[axis]) continue;
     Box bin_bounds[kBins];
     uint32_t bin_count[kBins] = {0};
-    for (uint32_t i = g.begin; i < g.end; ++i) {
-      const int b = bin_of(g.centroid_bounds, prims[i].centroid, axis);
-      bin_bounds[b].grow(prims[i].bounds);
-      bin_count[b]++;
+    if (g.count() <= 2 * kScanGrain || g_scan_threads <= 1) {
+      for (uint32_t i = g.begin; i < g.end; ++i) {
+        const int b = bin_of(g.centroid_bounds, prims[i].centroid, axis);
+        bin_bounds[b].grow(prims[i].bounds);
+        bin_count[b]++;
+      }
+    } else {
+      struct Part {
+        Box bounds[kBins];
+        uint32_t count[kBins] = {0};
+      };
+      std::vector<Part> part((g.count() + kScanGrain - 1) / kScanGrain);
+      parallel_chunks(g.count(), kScanGrain, g_scan_threads, [&](size_t b0, size_t b1, size_t c) {
+        for (size_t i = g.begin + b0; i < g.begin + b1; ++i) {
+          const int b = bin_of(g.centroid_bounds, prims[i].centroid, axis);
+          part[c].bounds[b].grow(prims[i].bounds);
+          part[c].count[b]++;
+        }
+      });
+      for (const Part& q : part)
+        for (int b = 0; b < kBins; ++b) {
+          bin_bounds[b].grow(q.bounds[b]);
+          bin_count[b] += q.count[b];
+        }
     }
     // suffix unions once, prefix on the fly: same unions/counts as summing bins per candidate
     Box suffix[kBins];
@@ -202,12 +244,12 @@ struct Builder {
     return first;
   }
 
-  // returns local node index, or 0 with nothing emitted when the range is a leaf
-  uint32_t build(Subtree& out, const Range& g) {
+  // The children of the node a range becomes (binned_sah_builder.hpp:215-241): one SAH split, then
+  // the smallest-area child that still holds >= 8 primitives is re-split until there are 8 children.
+  // Returns 0 when the range is a leaf.
+  uint32_t node_children(const Range& g, Range child[kWidth]) {
     const Split s = find_split(prims, g);
     if (g.count() < kWidth || (float)g.count() <= 1.0f + s.cost) return 0;
-
-    Range child[kWidth];
     uint32_t nchild = 2;
     split_range(prims, s, g, child[0], child[1]);
     while (nchild < kWidth) {
@@ -228,6 +270,25 @@ struct Builder {
       child[pick] = l;
       child[nchild++] = r;
     }
+    return nchild;
+  }
+
+  static void set_child_bounds(RefNode& n, uint32_t i, const Range& c) {
+    n.bounds[i] = c.bounds.lo.x;
+    n.bounds[i + 8] = c.bounds.lo.y;
+    n.bounds[i + 16] = c.bounds.lo.z;
+    n.bounds[i + 24] = c.bounds.hi.x;
+    n.bounds[i + 32] = c.bounds.hi.y;
+    n.bounds[i + 40] = c.bounds.hi.z;
+  }
+
+  // One whole sub-tree, depth first on the calling thread: nodes in pre-order, a node's leaf packets
+  // after the packets of its sub-trees (binned_sah_builder.hpp:243-267).  Returns the local node index,
+  // or 0 with nothing emitted when the range is a leaf.
+  uint32_t build(Subtree& out, const Range& g) {
+    Range child[kWidth];
+    const uint32_t nchild = node_children(g, child);
+    if (nchild == 0) return 0;
 
     const uint32_t self = (uint32_t)out.nodes.size();
     out.nodes.emplace_back();
@@ -237,15 +298,9 @@ struct Builder {
     for (uint32_t i = 0; i < nchild; ++i) child_node[i] = build(out, child[i]);
 
     for (uint32_t i = 0; i < nchild; ++i) {
-      RefNode& n = out.nodes[self];
-      n.bounds[i] = child[i].bounds.lo.x;
-      n.bounds[i + 8] = child[i].bounds.lo.y;
-      n.bounds[i + 16] = child[i].bounds.lo.z;
-      n.bounds[i + 24] = child[i].bounds.hi.x;
-      n.bounds[i + 32] = child[i].bounds.hi.y;
-      n.bounds[i + 40] = child[i].bounds.hi.z;
+      set_child_bounds(out.nodes[self], i, child[i]);
       if (child_node[i]) {
-        n.offset[i] = child_node[i];
+        out.nodes[self].offset[i] = child_node[i];
       } else {
         const uint32_t first = emit_packets(out, child[i].begin, child[i].end);
         RefNode& n2 = out.nodes[self];
@@ -255,6 +310,119 @@ struct Builder {
       }
     }
     return self;
+  }
+};
+
+// ---- the parallel build ---------------------------------------------------------------------------------
+// The top of the tree (ranges of >= `grain` primitives) is expanded node by node into a skeleton of
+// Pieces; every smaller range is one task that builds its whole sub-tree depth first into a private
+// Subtree.  Afterwards the pieces are laid out in the reference's numbering (node: pre-order; packets:
+// sub-trees first, then the node's own leaves) by a size pass and an offset pass, and every task's arrays
+// are copied to their final place once, in parallel.  The result is the single-threaded recursion's, bit
+// for bit: sub-trees own disjoint slices of the primitive array and all scans are order-independent.
+struct Piece {
+  bool whole = false;  // a finished sub-tree (task) rather than one skeleton node
+  Subtree sub;         // whole: local numbering, root at 0; sub.is_leaf: the range is a leaf
+  Range range;
+  uint32_t nchild = 0;
+  Range child[kWidth];
+  std::unique_ptr<Piece> kid[kWidth];  // null: cannot be an inner node (fewer than 8 primitives)
+  uint64_t n_nodes = 0, n_packets = 0; // totals of this piece's sub-tree (size pass)
+  uint64_t node_base = 0, packet_base = 0;
+  bool leaf() const { return whole ? sub.is_leaf : nchild == 0; }
+};
+
+struct ParallelBuild {
+  Builder& b;
+  TaskBag& bag;
+  uint32_t grain;
+
+  void expand(Piece* p) {
+    if (p->range.count() < grain) {  // one task: the whole sub-tree
+      p->whole = true;
+      const uint32_t root = b.build(p->sub, p->range);
+      p->sub.is_leaf = (root == 0 && p->sub.nodes.empty());
+      return;
+    }
+    p->nchild = b.node_children(p->range, p->child);
+    for (uint32_t i = 0; i < p->nchild; ++i) {
+      if (p->child[i].count() < kWidth) continue;  // a leaf for certain
+      p->kid[i].reset(new Piece());
+      Piece* k = p->kid[i].get();
+      k->range = p->child[i];
+      bag.add([this, k] { expand(k); });
+    }
+  }
+
+  static uint64_t leaf_packets(const Range& r) { return (r.count() + kWidth - 1) / kWidth; }
+
+  void measure(Piece* p) {
+    if (p->whole) {
+      p->n_nodes = p->sub.nodes.size();
+      p->n_packets = p->sub.packets.size();
+      return;
+    }
+    if (p->nchild == 0) return;
+    p->n_nodes = 1;
+    for (uint32_t i = 0; i < p->nchild; ++i) {
+      Piece* k = p->kid[i].get();
+      if (k) measure(k);
+      if (k && !k->leaf()) {
+        p->n_nodes += k->n_nodes;
+        p->n_packets += k->n_packets;
+      } else {
+        p->n_packets += leaf_packets(p->child[i]);
+      }
+    }
+  }
+
+  // offsets top-down; skeleton nodes and their leaf packets are written here, tasks are collected for
+  // the parallel copy
+  void place(Piece* p, uint64_t node_base, uint64_t packet_base, std::vector<RefNode>& nodes, std::vector<RefPacket>& packets,
+             std::vector<Piece*>& tasks) {
+    p->node_base = node_base;
+    p->packet_base = packet_base;
+    if (p->whole) {
+      tasks.push_back(p);
+      return;
+    }
+    RefNode& n = nodes[node_base];
+    init_ref_node(n);
+    uint64_t cn = node_base + 1, cp = packet_base;
+    for (uint32_t i = 0; i < p->nchild; ++i) {
+      Builder::set_child_bounds(n, i, p->child[i]);
+      Piece* k = p->kid[i].get();
+      if (k && !k->leaf()) {
+        n.offset[i] = (uint32_t)cn;
+        place(k, cn, cp, nodes, packets, tasks);
+        cn += k->n_nodes;
+        cp += k->n_packets;
+      }
+    }
+    for (uint32_t i = 0; i < p->nchild; ++i) {
+      Piece* k = p->kid[i].get();
+      if (k && !k->leaf()) continue;
+      Subtree tmp;
+      b.emit_packets(tmp, p->child[i].begin, p->child[i].end);
+      std::copy(tmp.packets.begin(), tmp.packets.end(), packets.begin() + cp);
+      n.flags[i] = 1;
+      n.offset[i] = (uint32_t)cp;
+      n.num[i] = (uint8_t)p->child[i].count();
+      cp += tmp.packets.size();
+    }
+  }
+
+  static void copy_task(const Piece* p, std::vector<RefNode>& nodes, std::vector<RefPacket>& packets) {
+    const uint32_t nb = (uint32_t)p->node_base, pb = (uint32_t)p->packet_base;
+    for (size_t j = 0; j < p->sub.nodes.size(); ++j) {
+      RefNode n = p->sub.nodes[j];
+      for (uint32_t i = 0; i < kWidth; ++i) {
+        if (n.bounds[i] > n.bounds[i + 24]) continue;  // unused slot (init_ref_node)
+        n.offset[i] += n.flags[i] == 1 ? pb : nb;
+      }
+      nodes[nb + j] = n;
+    }
+    std::copy(p->sub.packets.begin(), p->sub.packets.end(), packets.begin() + pb);
   }
 };
 
@@ -306,28 +474,47 @@ extern "C" {
 
 phos_bvh* phos_bvh_build(const phos_scene_desc* scene, int threads) {
   using namespace phos;
-  (void)threads;
   if (!scene) return nullptr;
+  const int nthreads = threads > 0 ? std::min(threads, 64) : worker_count();
+  uint32_t grain = 1u << 15;  // ranges below this are one task (PHOS_BUILD_GRAIN: tests use a tiny one)
+  if (const char* e = std::getenv("PHOS_BUILD_GRAIN")) grain = (uint32_t)std::max(8, std::atoi(e));
   const auto t0 = std::chrono::steady_clock::now();
   std::vector<Tri> tris;
   gather_triangles(scene, tris);
   std::vector<Prim> prims(tris.size());
-  for (size_t i = 0; i < tris.size(); ++i) {
-    Prim& p = prims[i];
-    p.index = (uint32_t)i;
-    p.bounds.grow(tris[i].a);
-    p.bounds.grow(tris[i].b);
-    p.bounds.grow(tris[i].c);
-    p.centroid = {(p.bounds.hi.x + p.bounds.lo.x) / 2, (p.bounds.hi.y + p.bounds.lo.y) / 2,
-                  (p.bounds.hi.z + p.bounds.lo.z) / 2};
-  }
+  parallel_chunks(tris.size(), 1u << 16, nthreads, [&](size_t b0, size_t b1, size_t) {
+    for (size_t i = b0; i < b1; ++i) {
+      Prim& p = prims[i];
+      p.index = (uint32_t)i;
+      p.bounds.grow(tris[i].a);
+      p.bounds.grow(tris[i].b);
+      p.bounds.grow(tris[i].c);
+      p.centroid = {(p.bounds.hi.x + p.bounds.lo.x) / 2, (p.bounds.hi.y + p.bounds.lo.y) / 2,
+                    (p.bounds.hi.z + p.bounds.lo.z) / 2};
+    }
+  });
   auto* out = new phos_bvh();
-  Subtree tree;
   Builder b{prims, tris};
-  const Range root = make_range(prims, 0, (uint32_t)prims.size());
-  b.build(tree, root);
-  out->nodes.swap(tree.nodes);
-  out->packets.swap(tree.packets);
+  g_scan_threads = nthreads;
+  Piece top;
+  top.range = make_range(prims, 0, (uint32_t)prims.size());
+  {
+    TaskBag bag;
+    ParallelBuild pb{b, bag, grain};
+    bag.add([&] { pb.expand(&top); });
+    bag.run(nthreads);
+    pb.measure(&top);
+    if (!top.leaf()) {
+      out->nodes.resize(top.n_nodes);
+      out->packets.resize(top.n_packets);
+      std::vector<Piece*> tasks;
+      pb.place(&top, 0, 0, out->nodes, out->packets, tasks);
+      parallel_chunks(tasks.size(), 1, nthreads, [&](size_t t0, size_t t1, size_t) {
+        for (size_t t = t0; t < t1; ++t) ParallelBuild::copy_task(tasks[t], out->nodes, out->packets);
+      });
+    }
+  }
+  g_scan_threads = 1;
   out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return out;
 }

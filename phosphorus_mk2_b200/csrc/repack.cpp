@@ -37,6 +37,7 @@
 #include <numeric>
 #include <thread>
 
+#include "host_parallel.hpp"
 #include "phos_internal.hpp"
 
 namespace phos {
@@ -97,32 +98,6 @@ struct Range {
   uint32_t tris = 0;
   uint32_t count() const { return end - begin; }
 };
-
-// ---- a minimal fork-join helper: the re-pack of a 10 M-triangle scene is ~20 s on one core ---------------
-int worker_count() {
-  int t = (int)std::thread::hardware_concurrency();
-  if (const char* e = std::getenv("PHOS_THREADS")) t = std::atoi(e);
-  return std::max(1, std::min(t, 64));
-}
-
-// fn(chunk_begin, chunk_end, chunk_index) over [0, n) in chunks of `grain`
-template <class F>
-void parallel_chunks(size_t n, size_t grain, int threads, F&& fn) {
-  const size_t chunks = (n + grain - 1) / grain;
-  if (threads <= 1 || chunks <= 1) {
-    for (size_t c = 0; c < chunks; ++c) fn(c * grain, std::min(n, (c + 1) * grain), c);
-    return;
-  }
-  std::atomic<size_t> next{0};
-  auto body = [&]() {
-    for (size_t c; (c = next.fetch_add(1)) < chunks;) fn(c * grain, std::min(n, (c + 1) * grain), c);
-  };
-  std::vector<std::thread> pool;
-  const int extra = (int)std::min<size_t>((size_t)threads, chunks) - 1;
-  for (int t = 0; t < extra; ++t) pool.emplace_back(body);
-  body();
-  for (auto& t : pool) t.join();
-}
 
 struct Bins {
   DBox box[3][kBins];

@@ -171,26 +171,29 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   r.flags = 0;
   rd.oct = 0;
   uint32_t ridx = 0;
-  bool has_ray = false, changed = false;
+  bool has_ray = false;
   uint2 cur = make_uint2(0u, 0u);
-  uint32_t trem = 0, tptr = 0, lmask = 0, lcounts = 0, lbase = 0;
+  // leaf state: `lt` = hit leaf slots of the current node still to open (key space, bits 0-7) | triangles left
+  // in the open leaf (bits 8-11); tptr = next triangle; lcounts / lbase = the node's leaf table
+  uint32_t lt = 0, tptr = 0, lcounts = 0, lbase = 0;
   uint32_t n_nodes = 0, n_tris = 0;
 
   for (;;) {
     // 1. what every lane wants to do next (two ballots drive everything else)
-    const bool tri_work = has_ray && (trem | lmask) != 0u;
+    const bool tri_work = has_ray && lt != 0u;
     const bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
     const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
     const unsigned nl = __ballot_sync(0xffffffffu, node_work);
     // 2. enough lanes without work (finished rays or empty lanes): retire and refill from the chunk
     if (__popc(~(tl | nl)) >= kRefillMin) {
       if (has_ray && !tri_work && !node_work) {
-        if (changed) {
+        if (r.tri != kNoTri) {  // something was accepted (accept_hit marks shadow rays too)
           P.rays.d[ridx] = r.d;
           P.rays.flags[ridx] = r.flags;
           if (!(r.flags & PHOS_SHADOW)) {
-            P.rays.mesh[ridx] = r.mesh;
-            P.rays.face[ridx] = r.face;
+            const uint4 ids = __ldg(P.accel.tris + 3ull * r.tri + 2);  // changed and not SHADOW: a triangle is held
+            P.rays.mesh[ridx] = ids.y;
+            P.rays.face[ridx] = ids.z;
             P.rays.u[ridx] = r.u;
             P.rays.v[ridx] = r.v;
           }
@@ -215,15 +218,13 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
               r.wz = __uint_as_float(stage[cur_buf][5][k]);
               r.d = __uint_as_float(stage[cur_buf][6][k]);
               r.flags = fl;
-              r.order = 0xffffffffu;
-              r.mesh = r.face = 0u;
+              r.tri = kNoTri;
               r.u = r.v = 0.0f;
               rd = make_raydir(r.wx, r.wy, r.wz);
               ridx = cur_base + k;
               cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
               sp = 0;
-              trem = lmask = 0u;
-              changed = false;
+              lt = 0u;
               has_ray = true;
             }
           }
@@ -238,18 +239,19 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
     // a triangle step is cheaper than a node step: PHOS_TRI_BIAS weights the vote
     if (PHOS_TRI_BIAS * __popc(tl) >= __popc(nl)) {
       if (tri_work) {
-        if (trem == 0u) {  // open the next hit leaf, nearest octant first
-          const uint32_t slot = (__ffs(lmask) - 1) ^ rd.oct;
-          lmask &= lmask - 1u;
-          trem = (lcounts >> (4u * slot)) & 15u;  // 0 for an empty slot
+        if ((lt >> 8) == 0u) {  // open the next hit leaf, nearest octant first
+          const uint32_t slot = (__ffs(lt) - 1) ^ rd.oct;
+          lt &= lt - 1u;
+          lt |= ((lcounts >> (4u * slot)) & 15u) << 8;  // 0 for an empty slot
           tptr = lbase + nibble_prefix(lcounts, slot);
         }
-        if (trem) {
+        if (lt >> 8) {
           const uint4* tp = P.accel.tris + 3ull * tptr;
+          const uint32_t tptr0 = tptr;
           const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
 #if PHOS_TRI_PAIR
           // two triangles of the leaf per step: both 48-byte fetches are in flight together
-          const bool two = trem >= 2u;
+          const bool two = lt >= 0x200u;
           uint4 a2 = a, b2 = b, c2 = c;
           if (two) {
             a2 = __ldg(tp + 3);
@@ -257,28 +259,24 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
             c2 = __ldg(tp + 5);
           }
           tptr += two ? 2u : 1u;
-          trem -= two ? 2u : 1u;
+          lt -= two ? 0x200u : 0x100u;
           if (kCount) n_tris += two ? 2u : 1u;
 #else
           const bool two = false;
           const uint4 a2 = a, b2 = b, c2 = c;
           ++tptr;
-          --trem;
+          lt -= 0x100u;
           if (kCount) ++n_tris;
 #endif
           float ds, us, vs;
           bool done = false;
-          if (mt_triangle(a, b, c, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) && accept_hit(r, ds, us, vs, c)) {
-            changed = true;
+          if (mt_triangle(a, b, c, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) && accept_hit(P.accel, r, ds, us, vs, tptr0))
             done = (r.flags & PHOS_SHADOW) != 0u;
-          }
           if (two && !done && mt_triangle(a2, b2, c2, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) &&
-              accept_hit(r, ds, us, vs, c2)) {
-            changed = true;
+              accept_hit(P.accel, r, ds, us, vs, tptr0 + 1u))
             done = (r.flags & PHOS_SHADOW) != 0u;
-          }
           if (done) {  // any-hit: this ray is finished
-            trem = lmask = 0u;
+            lt = 0u;
             cur.y = 0u;
             sp = 0;
           }
@@ -291,7 +289,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
         if (cur.y >> 8) push(cur);
         const NodeHits h = node_test(P.accel, node, r.ox, r.oy, r.oz, rd, r.d * PHOS_CULL_SLACK);
         if (kCount) ++n_nodes;
-        lmask = h.leaf;
+        lt = h.leaf;
         lcounts = h.counts;
         lbase = h.tri_base;
         cur = make_uint2(h.child_base, h.imask | (h.inner << 8));

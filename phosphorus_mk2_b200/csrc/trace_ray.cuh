@@ -51,10 +51,13 @@ struct Ray {
   float wx, wy, wz;
   float d;
   uint32_t flags;
-  // hit record
-  uint32_t mesh, face, order;
+  // hit record: the triangle (index into the packed array; its ids and tie-break order are read back from
+  // there when needed — three registers fewer per ray than carrying mesh, face and order) and u, v
+  uint32_t tri;
   float u, v;
 };
+
+constexpr uint32_t kNoTri = 0xffffffffu;
 
 // per-ray constants of the slab test
 struct RayDir {
@@ -225,21 +228,26 @@ __device__ __forceinline__ uint32_t take_child(uint2& group, uint32_t oct) {
   return group.x + __popc(group.y & ((1u << slot) - 1u) & 0xffu);
 }
 
-// closest-hit / any-hit acceptance of one Möller–Trumbore result; returns true when r changed
-__device__ __forceinline__ bool accept_hit(Ray& r, float ds, float us, float vs, const uint4 c) {
+__device__ __forceinline__ uint32_t tri_order(const DevAccel& A, uint32_t tri) {
+  return __ldg(reinterpret_cast<const uint32_t*>(A.tris + 3ull * tri + 2) + 3);
+}
+
+// closest-hit / any-hit acceptance of one Möller–Trumbore result against triangle `tri`; returns true
+// when r changed.  An exact tie in t goes to the lower GTri::order; both orders are fetched only then
+// (ties are rare, and nothing stays live in a register for them).
+__device__ __forceinline__ bool accept_hit(const DevAccel& A, Ray& r, float ds, float us, float vs, uint32_t tri) {
   if (r.flags & PHOS_SHADOW) {
     if (!(ds < r.d)) return false;
     r.d = ds;
+    r.tri = tri;  // "something was accepted": the surface record of a shadow ray is never written
     r.flags |= PHOS_HIT;
     return true;
   }
-  if (ds < r.d || (ds == r.d && (r.flags & PHOS_HIT) && c.w < r.order)) {
+  if (ds < r.d || (ds == r.d && r.tri != kNoTri && tri_order(A, tri) < tri_order(A, r.tri))) {
     r.d = ds;
     r.u = us;
     r.v = vs;
-    r.mesh = c.y;
-    r.face = c.z;
-    r.order = c.w;
+    r.tri = tri;
     r.flags |= PHOS_HIT;
     return true;
   }
@@ -271,13 +279,14 @@ __device__ __forceinline__ bool trace_ray(const DevAccel& A, Ray& r, Stack& st, 
       const uint32_t lslot = (__ffs(h.leaf) - 1) ^ rd.oct;
       h.leaf &= h.leaf - 1;
       const uint32_t cnt = (h.counts >> (4 * lslot)) & 15u;  // 0 for an empty slot
-      const uint4* tp = A.tris + 3ull * (h.tri_base + nibble_prefix(h.counts, lslot));
+      const uint32_t first = h.tri_base + nibble_prefix(h.counts, lslot);
+      const uint4* tp = A.tris + 3ull * first;
       for (uint32_t k = 0; k < cnt; ++k, tp += 3) {
         const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         if (kCount) ++*n_tris;
         float ds, us, vs;
         if (!mt_triangle(a, b, c, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs)) continue;
-        if (accept_hit(r, ds, us, vs, c)) {
+        if (accept_hit(A, r, ds, us, vs, first + k)) {
           changed = true;
           if (r.flags & PHOS_SHADOW) return true;
         }

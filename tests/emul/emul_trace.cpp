@@ -21,6 +21,7 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline uint4 __ldg(const uint4* p) { return *p; }
+static inline uint32_t __ldg(const uint32_t* p) { return *p; }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
@@ -66,15 +67,15 @@ int emul_trace(const void* nodes288, uint32_t n_nodes, const void* packets384, u
     r.ox = rays->px[i]; r.oy = rays->py[i]; r.oz = rays->pz[i];
     r.wx = rays->wx[i]; r.wy = rays->wy[i]; r.wz = rays->wz[i];
     r.d = rays->d[i];
-    r.order = 0xffffffffu;
-    r.mesh = r.face = 0u;
+    r.tri = kNoTri;
     r.u = r.v = 0.0f;
     nn = nt = 0;
     if (trace_ray<true>(A, r, st, &nn, &nt)) {
       rays->d[i] = r.d;
       rays->flags[i] = r.flags;
       if (!(r.flags & PHOS_SHADOW)) {
-        rays->mesh[i] = r.mesh; rays->face[i] = r.face; rays->u[i] = r.u; rays->v[i] = r.v;
+        const uint4 ids = A.tris[3ull * r.tri + 2];
+        rays->mesh[i] = ids.y; rays->face[i] = ids.z; rays->u[i] = r.u; rays->v[i] = r.v;
       }
     }
     tn += nn;

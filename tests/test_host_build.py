@@ -47,6 +47,23 @@ def test_host_build_is_bit_identical_to_live_reference(reflib, make):
     assert_same_tree(rn, rp, a.nodes_array(), a.packets_array())
 
 
+def test_parallel_build_equals_single_threaded_build(monkeypatch):
+    """phos_bvh_build expands the top of the tree into a skeleton, builds every range below
+    PHOS_BUILD_GRAIN primitives as an independent task and lays the pieces out with prefix offsets: the
+    arrays must be those of the plain depth-first recursion for any grain / thread count."""
+    sc = scenes.heightfield(160, seed=5)  # 51 k triangles
+    monkeypatch.setenv("PHOS_BUILD_GRAIN", "2000000000")
+    monkeypatch.setenv("PHOS_THREADS", "1")
+    a = Accel(sc)
+    n0, p0 = a.nodes_array(), a.packets_array()
+    for grain, threads in (("8", "4"), ("100", "3"), ("5000", "8")):
+        monkeypatch.setenv("PHOS_BUILD_GRAIN", grain)
+        monkeypatch.setenv("PHOS_THREADS", threads)
+        b = Accel(sc)
+        assert_same_tree(n0, p0, b.nodes_array(), b.packets_array())
+        assert np.array_equal(p0, b.packets_array())
+
+
 def test_fewer_than_eight_triangles_builds_no_node():
     """The reference builder returns 0 at the root for < 8 primitives (binned_sah_builder.hpp:220):
     no node at all.  The host build mirrors that; upload then rejects the empty structure."""
