@@ -445,7 +445,7 @@ def main():
                            "timing": "CUDA events around the traversal kernel, summed over steps, max over ranks",
                            "hit_fraction": hits / n, "preprocess_s": prep_s, "wall_s_timed_loop": wall},
                 "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 24 * n,
+                "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 8 * n + 16 * hits,
                         "steps": e2e_steps, "matches_device_path": e2e_ok},
                 "roofline": roof, "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line), flush=True)

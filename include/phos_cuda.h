@@ -110,9 +110,14 @@ int phos_cuda_accel_stats(phos_ctx* ctx, phos_accel_stats* out);
  *   MASKED            -> not traced, untouched;
  *   SHADOW            -> any-hit: on an accepted hit set HIT and shrink d, leave mesh/face/u/v alone;
  *   otherwise         -> closest hit: set HIT, d, mesh, face, u, v.
- * `rays` holds HOST pointers; the call copies all twelve arrays in (48 B/ray: the surface record of
- * a ray that is not hit must come back as it was), traces, copies out d, flags, mesh, face, u, v
- * (24 B/ray), chunked so copies overlap traversal.  Blocking. */
+ * `rays` holds HOST pointers; the call is chunked so copies overlap traversal.  Blocking.
+ *   - page-locked arrays from phos_cuda_host_alloc laid out as one slab at a constant stride in the order
+ *     px, py, pz, wx, wy, wz, d, flags, mesh, face, u, v (or any cudaHostAlloc / cudaHostRegister memory
+ *     laid out like that): the eight input arrays go up (32 B/ray), d and flags come back for every ray and
+ *     the surface record only where the traversal wrote one, stored straight into the caller's arrays
+ *     (8 B/ray + 16 B per closest hit);
+ *   - any other host memory: all twelve arrays go up (48 B/ray: the surface record of a ray that is not
+ *     hit must come back as it was) and d, flags, mesh, face, u, v come back (24 B/ray). */
 int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n);
 /* Same, `rays` holds DEVICE pointers of this ctx's device; asynchronous on the ctx stream. */
 int phos_cuda_trace_device(phos_ctx* ctx, const phos_rays* rays, uint64_t n);

@@ -10,9 +10,9 @@
 namespace phos {
 
 constexpr int kPipe = 4;                     // host-pointer trace: chunks in flight
-constexpr uint64_t kPipeChunk = 1ull << 17;  // rays per chunk (6 MiB in, 3 MiB out): measured best on the B200 box —
-                                             // smaller chunks are bound by the ~20 us the host pays per copy call,
-                                             // larger ones overlap less of the up-link, the SMs and the down-link
+constexpr uint64_t kPipeChunk = 1ull << 18;  // rays per chunk (8 MiB in): measured best on the B200 box — smaller
+                                             // chunks are bound by the ~20 us the host pays per copy call, larger
+                                             // ones overlap less of the up-link, the SMs and the down-link
 
 // One staging slot of the host-pointer trace pipeline.  Copies in, traversal and copies out run on three
 // DEDICATED streams (phos_ctx::s_in / s_cmp / s_out) chained by these events: with one stream per slot the

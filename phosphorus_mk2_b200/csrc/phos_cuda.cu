@@ -45,14 +45,60 @@ bool alloc_rays(phos_ctx* ctx, uint64_t n, phos_rays& out) {
   const uint64_t stride = (n * 4 + 255) / 256 * 256;
   char* base = nullptr;
   if (!cuda_ok(ctx, cudaMalloc(&base, std::max<uint64_t>(stride, 256) * 12), "cudaMalloc(ray stream)")) return false;
+  // slab order: the eight arrays a query reads first, then the surface record
   float** f[] = {&out.px, &out.py, &out.pz, &out.wx, &out.wy, &out.wz, &out.d};
   for (int i = 0; i < 7; ++i) *f[i] = (float*)(base + stride * i);
-  out.mesh = (uint32_t*)(base + stride * 7);
-  out.face = (uint32_t*)(base + stride * 8);
-  out.u = (float*)(base + stride * 9);
-  out.v = (float*)(base + stride * 10);
-  out.flags = (uint32_t*)(base + stride * 11);
+  out.flags = (uint32_t*)(base + stride * 7);
+  out.mesh = (uint32_t*)(base + stride * 8);
+  out.face = (uint32_t*)(base + stride * 9);
+  out.u = (float*)(base + stride * 10);
+  out.v = (float*)(base + stride * 11);
   return true;
+}
+
+// Results of one pipeline chunk straight into the caller's page-locked arrays (zero-copy stores over
+// PCIe): d and flags for every ray, the surface record only where the traversal wrote one — the staging
+// `mesh` row is preset to 0xffffffff, a value no hit can produce (mesh ids are 16 + 16 bits below 0xffff,
+// reference src/triangle.hpp:28-31).  That is what lets the up-link carry 32 B per ray instead of 48: the
+// surface record of rays that miss, and of shadow rays (it holds the sampled light's ids, spt.hpp:120-124),
+// never has to visit the device to come back untouched.  Four rays per thread, 16-byte stores, grid-stride.
+__global__ void __launch_bounds__(256) writeback_kernel(const phos_rays dev, const phos_rays host, uint32_t n) {
+ for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; i < n; i += gridDim.x * blockDim.x * 4u) {
+  if (i + 4u <= n) {
+    const uint4 m = *reinterpret_cast<const uint4*>(dev.mesh + i);
+    *reinterpret_cast<float4*>(host.d + i) = *reinterpret_cast<const float4*>(dev.d + i);
+    *reinterpret_cast<uint4*>(host.flags + i) = *reinterpret_cast<const uint4*>(dev.flags + i);
+    const bool all4 = m.x != 0xffffffffu && m.y != 0xffffffffu && m.z != 0xffffffffu && m.w != 0xffffffffu;
+    if (all4) {
+      *reinterpret_cast<uint4*>(host.mesh + i) = m;
+      *reinterpret_cast<uint4*>(host.face + i) = *reinterpret_cast<const uint4*>(dev.face + i);
+      *reinterpret_cast<float4*>(host.u + i) = *reinterpret_cast<const float4*>(dev.u + i);
+      *reinterpret_cast<float4*>(host.v + i) = *reinterpret_cast<const float4*>(dev.v + i);
+      continue;
+    }
+    const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k)
+      if (mm[k] != 0xffffffffu) {
+        host.mesh[i + k] = mm[k];
+        host.face[i + k] = dev.face[i + k];
+        host.u[i + k] = dev.u[i + k];
+        host.v[i + k] = dev.v[i + k];
+      }
+    continue;
+  }
+  for (uint32_t k = i; k < n; ++k) {
+    host.d[k] = dev.d[k];
+    host.flags[k] = dev.flags[k];
+    const uint32_t m = dev.mesh[k];
+    if (m != 0xffffffffu) {
+      host.mesh[k] = m;
+      host.face[k] = dev.face[k];
+      host.u[k] = dev.u[k];
+      host.v[k] = dev.v[k];
+    }
+  }
+ }
 }
 
 static const void* in_ptr(const phos_rays& r, int k) {
@@ -249,6 +295,7 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
   cudaSetDevice(ctx->device);
   uint64_t chunk = std::min<uint64_t>(kPipeChunk, std::max<uint64_t>(32768, (n + 2 * kPipe - 1) / (2 * kPipe)));
   if (const char* e = std::getenv("PHOS_PIPE_CHUNK")) chunk = std::max<uint64_t>(1024, std::strtoull(e, nullptr, 10));  // tuning
+  chunk = (chunk + 1023) / 1024 * 1024;  // chunk starts stay 16-byte aligned (TMA staging, 16-byte write-back stores)
   for (int i = 0; i < kPipe; ++i) {
     ctx->pipe[i].used = false;
     if (ctx->pipe[i].capacity < chunk) {
@@ -259,26 +306,51 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
       ctx->pipe[i].capacity = chunk;
     }
   }
-  // A stream whose twelve arrays sit in one slab at a constant stride (px, py, pz, wx, wy, wz, d, mesh, face,
-  // u, v, flags — what phos_cuda_host_alloc-based callers and phos_cuda_rays_alloc produce) moves with ONE
+  // A stream whose twelve arrays sit in one slab at a constant stride (px, py, pz, wx, wy, wz, d, flags, mesh,
+  // face, u, v — what phos_cuda_host_alloc-based callers and phos_cuda_rays_alloc produce) moves with ONE
   // pitched copy per chunk and direction instead of 12 + 6: every copy call costs the host ~20 us here,
   // as much as the wire time of a 1 MB array, so the call count, not PCIe, was the limit.
-  const char* slab[12] = {(const char*)rays->px, (const char*)rays->py, (const char*)rays->pz, (const char*)rays->wx,
-                          (const char*)rays->wy, (const char*)rays->wz, (const char*)rays->d,  (const char*)rays->mesh,
-                          (const char*)rays->face, (const char*)rays->u, (const char*)rays->v, (const char*)rays->flags};
+  const char* slab[12] = {(const char*)rays->px, (const char*)rays->py, (const char*)rays->pz,    (const char*)rays->wx,
+                          (const char*)rays->wy, (const char*)rays->wz, (const char*)rays->d,     (const char*)rays->flags,
+                          (const char*)rays->mesh, (const char*)rays->face, (const char*)rays->u, (const char*)rays->v};
   const ptrdiff_t hstride = slab[1] - slab[0];
   bool pitched = hstride >= (ptrdiff_t)(n * 4);
   for (int k = 2; pitched && k < 12; ++k) pitched = slab[k] - slab[k - 1] == hstride;
+  // Page-locked, device-mapped host arrays (cudaHostAlloc / cudaHostRegister; under unified addressing the
+  // device pointer is the host pointer): only the eight input arrays go up (32 B per ray) and the results are
+  // stored straight into the caller's arrays by writeback_kernel.  Anything else (pageable memory) takes the
+  // copy-everything path: 48 B per ray up so that untouched surface records come back as they were, 24 B down.
+  bool sparse = pitched && (((uintptr_t)slab[0] | (uintptr_t)hstride) & 15u) == 0 && chunk % 4 == 0;
+  if (const char* e = std::getenv("PHOS_E2E_SPARSE")) sparse = sparse && std::atoi(e) != 0;
+  if (sparse) {
+    cudaPointerAttributes at;
+    memset(&at, 0, sizeof(at));
+    const char* last = slab[11] + (n - 1) * 4;
+    sparse = cudaPointerGetAttributes(&at, slab[0]) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+             at.devicePointer == (void*)slab[0];
+    sparse = sparse && cudaPointerGetAttributes(&at, last) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+             at.devicePointer == (void*)last;
+    cudaGetLastError();  // an unregistered pointer reports an error on older drivers: not ours
+  }
   int slot = 0;
   bool ok = true;
+  // The write-back runs on a handful of CTAs: its posted writes share the link's outbound queue with the read
+  // requests of the up-copies, and a full grid starves them (measured, profiles/r01_e2e_pipeline.log: 4 CTAs
+  // 1.84 ms per 2 M-ray frame, a full grid 2.06-2.24 ms; moving d / flags by copy engine instead changes nothing).
+  int wb_ctas = 4;
+  if (const char* e = std::getenv("PHOS_E2E_WB_CTAS")) wb_ctas = std::max(1, std::atoi(e));
+  const char* dbg = std::getenv("PHOS_E2E_DEBUG");  // timing probes only (tools/e2e_probe.py): "noin" / "noout" skip a stage
+  const bool dbg_noin = dbg && strstr(dbg, "noin"), dbg_noout = dbg && strstr(dbg, "noout");
   for (uint64_t base = 0; ok && base < n; base += chunk, slot = (slot + 1) % kPipe) {
     const uint64_t cnt = std::min(chunk, n - base);
     PipeLane& L = ctx->pipe[slot];
     const size_t dstride = (size_t)((const char*)L.rays.py - (const char*)L.rays.px);
     if (L.used) ok = cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_in, L.ev_out, 0), "pipeline wait");  // slot free again
-    if (ok && pitched)
-      ok = cuda_ok(ctx, cudaMemcpy2DAsync(L.rays.px, dstride, slab[0] + base * 4, (size_t)hstride, cnt * 4, 12, cudaMemcpyHostToDevice, ctx->s_in),
+    if (ok && pitched && !dbg_noin)
+      ok = cuda_ok(ctx, cudaMemcpy2DAsync(L.rays.px, dstride, slab[0] + base * 4, (size_t)hstride, cnt * 4, sparse ? 8 : 12,
+                                          cudaMemcpyHostToDevice, ctx->s_in),
                    "H2D rays");
+    if (ok && sparse) ok = cuda_ok(ctx, cudaMemsetAsync(L.rays.mesh, 0xff, cnt * 4, ctx->s_in), "memset(mesh)");
     for (int k = 0; ok && !pitched && k < 12; ++k) {
       const char* src = (const char*)in_ptr(*rays, k) + base * 4;
       ok = cuda_ok(ctx, cudaMemcpyAsync((void*)in_ptr(L.rays, k), src, cnt * 4, cudaMemcpyHostToDevice, ctx->s_in), "H2D rays");
@@ -290,9 +362,21 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
     if (rc) return rc;
     ok = cuda_ok(ctx, cudaEventRecord(L.ev_cmp, ctx->s_cmp), "pipeline record") &&
          cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_out, L.ev_cmp, 0), "pipeline wait");
-    if (ok && pitched)  // rows 6..11 of the slab: d, mesh, face, u, v, flags
+    if (ok && sparse && !dbg_noout) {
+      phos_rays h = *rays;
+      float** hf[] = {&h.px, &h.py, &h.pz, &h.wx, &h.wy, &h.wz, &h.d, &h.u, &h.v};
+      for (float** q : hf) *q += base;
+      h.mesh += base;
+      h.face += base;
+      h.flags += base;
+      const unsigned full = (unsigned)((cnt + 1023) / 1024);
+      writeback_kernel<<<std::min<unsigned>(full, (unsigned)wb_ctas), 256, 0, ctx->s_out>>>(L.rays, h, (uint32_t)cnt);
+      ctx->launches++;
+      ok = cuda_ok(ctx, cudaGetLastError(), "writeback_kernel launch");
+    } else if (ok && pitched && !dbg_noout) {  // rows 6..11 of the slab: d, flags, mesh, face, u, v
       ok = cuda_ok(ctx, cudaMemcpy2DAsync((void*)(slab[6] + base * 4), (size_t)hstride, L.rays.d, dstride, cnt * 4, 6, cudaMemcpyDeviceToHost, ctx->s_out),
                    "D2H rays");
+    }
     for (int k = 0; ok && !pitched && k < 6; ++k) {
       char* dst = (char*)out_ptr(*rays, k) + base * 4;
       ok = cuda_ok(ctx, cudaMemcpyAsync(dst, out_ptr(L.rays, k), cnt * 4, cudaMemcpyDeviceToHost, ctx->s_out), "D2H rays");

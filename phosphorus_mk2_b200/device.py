@@ -272,7 +272,7 @@ def pinned_ray_batch(n: int) -> RayBatch:
     r._pinned = base
     # one slab, constant stride, in the library's own array order: phos_cuda_trace then moves a chunk with a
     # single pitched copy per direction (see csrc/phos_cuda.cu)
-    order = ("px", "py", "pz", "wx", "wy", "wz", "d", "mesh", "face", "u", "v", "flags")
+    order = ("px", "py", "pz", "wx", "wy", "wz", "d", "flags", "mesh", "face", "u", "v")
     for i, k in enumerate(order):
         ct = C.c_uint32 if k in ("mesh", "face", "flags") else C.c_float
         arr = np.ctypeslib.as_array(C.cast(base + stride * i, C.POINTER(ct)), (n,))

@@ -57,6 +57,44 @@ def test_pinned_host_stream_and_odd_lengths(device, oracle):
         assert len(mismatches(src, pr, want)) == 0, n
 
 
+def test_pinned_stream_sparse_write_back(device, oracle, monkeypatch):
+    """Page-locked, device-mapped host arrays take the 32 B/ray up-link path: the surface record is stored
+    straight into the caller's arrays only where the traversal wrote one.  Mixed closest-hit / shadow /
+    masked rays with recognisable stale surface records, several pipeline chunks and a ragged tail; the
+    copy-everything path (PHOS_E2E_SPARSE=0) must give the same arrays."""
+    sc = scenes.heightfield(96)
+    acc = Accel(sc)
+    device.preprocess(sc, acc)
+    nodes, packets = acc.nodes_array(), acc.packets_array()
+    monkeypatch.setenv("PHOS_PIPE_CHUNK", "4096")
+    n = 4096 * 5 + 1237
+    src = raysets.aimed_rays(sc, n, seed=77)
+    rnd = raysets.random_rays(sc, n, seed=78)  # many misses
+    for f in ("px", "py", "pz", "wx", "wy", "wz"):
+        getattr(src, f)[1::3] = getattr(rnd, f)[1::3]
+    sh = raysets.as_shadow(src, seed=79, masked_fraction=0.2)
+    for f in ("d", "flags"):
+        getattr(src, f)[2::3] = getattr(sh, f)[2::3]
+    src.mesh[:] = 0xABCD0001  # stale records: must survive on misses, shadow and masked rays
+    src.face[:] = 777
+    src.u[:] = 0.25
+    src.v[:] = 0.5
+    want, _ = oracle.traverse(nodes, packets, src)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PHOS_E2E_SPARSE", mode)
+        pr = pinned_ray_batch(n)
+        for f in ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags"):
+            getattr(pr, f)[:] = getattr(src, f)
+        device.trace(pr)
+        assert len(mismatches(src, pr, want)) == 0, mode
+        got[mode] = pr
+    closest = (src.flags & 4) == 0
+    for f in ("d", "u", "v", "mesh", "face", "flags"):
+        a, b = bits(getattr(got["1"], f)), bits(getattr(got["0"], f))
+        assert np.array_equal(a[closest], b[closest]), f
+
+
 def test_empty_stream_and_call_order_errors(device):
     fresh = CudaDevice.make(Options(), 0)
     with pytest.raises(PhosError):
