@@ -155,6 +155,12 @@ int phos_cuda_upload_scene(phos_ctx* ctx, const phos_scene_desc* scene);
  * src/xpu/cpu.cpp:177); unlike the reference, partial tiles are not padded to 1024 slots. */
 int phos_cuda_camera_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, float jx, float jy,
                           const phos_rays* device_rays);
+/* The same with the thin lens of camera_t (aperture_radius != 0, src/entities/camera.hpp:37-39;
+ * camera.hpp:140-147): the lens sample of a ray is the renderer's own draw for (seed, film pixel, sample),
+ * so these are the primary rays phos_cuda_render traces for that sample.  phos_cuda_camera_rays is this
+ * call with seed 0, sample 0. */
+int phos_cuda_camera_rays_lens(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, float jx, float jy, uint64_t seed,
+                               uint32_t sample, const phos_rays* device_rays);
 
 /* tile_renderer_t::render_tile over a list of tiles (src/xpu/cpu.cpp:156-205), as a wavefront: path-trace
  * samples [spp_begin, spp_end) of every pixel of the given tiles and accumulate
@@ -179,6 +185,13 @@ int phos_cuda_film_device_ptr(phos_ctx* ctx, void** out_ptr, uint64_t* out_float
 /* copy a rectangle of the film to host as interleaved RGBA (alpha = 1 where rendered): the tile
  * buffer film_t<>::add_tile receives.  Blocking. */
 int phos_cuda_film_read(phos_ctx* ctx, float* rgba, uint32_t x, uint32_t y, uint32_t w, uint32_t h);
+/* render_buffer_t::NORMALS (src/buffer.hpp:10, src/xpu/cpu.cpp:97,194-196): per pixel the shading normal of the
+ * last sample whose primary ray hit (0 where none did).  Off by default; enabling allocates and clears a W*H*3
+ * float channel that phos_cuda_render then fills; read it back as interleaved xyz.  (Not part of the multi-GPU
+ * film reduce: under tile partitioning read each rank's own tiles; under sample partitioning the rank holding the
+ * last sample range has the reference's values.) */
+int phos_cuda_enable_normals(phos_ctx* ctx, int on);
+int phos_cuda_film_read_normals(phos_ctx* ctx, float* xyz, uint32_t x, uint32_t y, uint32_t w, uint32_t h);
 
 #ifdef __cplusplus
 }

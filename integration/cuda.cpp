@@ -162,11 +162,15 @@ void cuda_t::preprocess(const scene_t& scene) {
 void cuda_t::start(const scene_t&, frame_state_t& frame) {
   if (worker.joinable()) worker.join();  // a device is started once per view (session.cpp:224-229)
   check(ctx, phos_cuda_film_clear(ctx));
+  // the NORMALS channel only when the frame's tile format asks for it (render_buffer_t::NORMALS, cpu.cpp:97)
+  bool want_normals = false;
+  for (const auto& ch : frame.tiles->format.channels) want_normals = want_normals || ch.name == render_buffer_t::NORMALS;
+  check(ctx, phos_cuda_enable_normals(ctx, want_normals ? 1 : 0));
   frame_state_t* fs = &frame;
   worker = std::thread([this, fs] {
     allocator_t allocator(1024 * 1024 * 4);
     std::vector<phos_tile> chunk;
-    std::vector<float> rgba;
+    std::vector<float> rgba, nrm;
     job::tiles_t::tile_t t;
     for (;;) {
       chunk.clear();
@@ -185,6 +189,15 @@ void cuda_t::start(const scene_t&, frame_state_t& frame) {
               const float* p = &rgba[4u * (y * c.w + x)];
               primary->set(x, y, Imath::V3f(p[0], p[1], p[2]));
             }
+        if (auto* normals = buffer.channel(render_buffer_t::NORMALS)) {
+          nrm.resize(3u * c.w * c.h);
+          check(ctx, phos_cuda_film_read_normals(ctx, nrm.data(), c.x, c.y, c.w, c.h));
+          for (uint32_t y = 0; y < c.h; ++y)
+            for (uint32_t x = 0; x < c.w; ++x) {
+              const float* p = &nrm[3u * (y * c.w + x)];
+              normals->set(x, y, Imath::V3f(p[0], p[1], p[2]));
+            }
+        }
         fs->film->add_tile(Imath::V2i(c.x, c.y), Imath::V2i(c.w, c.h), buffer);
       }
     }

@@ -81,7 +81,7 @@ float orc_rnd(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, u
   h = orc_mix(h ^ (0xC2B2AE35u * (bounce * 8u + dim + 1u)));
   return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
-enum { DIM_LIGHT = 0, DIM_LIGHT_U = 1, DIM_LIGHT_V = 2, DIM_BSDF_U = 3, DIM_BSDF_V = 4, DIM_RR = 5, DIM_FILM = 7 };
+enum { DIM_LIGHT = 0, DIM_LIGHT_U = 1, DIM_LIGHT_V = 2, DIM_BSDF_U = 3, DIM_BSDF_V = 4, DIM_RR = 5, DIM_LENS = 6, DIM_FILM = 7 };
 
 /* film jitter per sample index: sample::stratified_2d (math/sampling.hpp:67-82) over
  * spd = lround(sqrt(spp)) strata per axis, as sampler_t::preprocess calls it (sampling.cpp:96-99).
@@ -343,6 +343,58 @@ static v3 simd_normalize(v3 a, int rcp_mode) {
   return V(a.x * ool, a.y * ool, a.z * ool);
 }
 
+/* camera::perspective_kernel_t for one pixel (kernels/cpu/camera.hpp:113-152): film jitter (jx, jy), lens
+ * sample (lu, lv) used only when aperture_radius != 0 (entities/camera.hpp:37-39).
+ * The thin lens follows the reference to the letter, including what looks like slips in
+ * simd::concentric_sample_disc (math/simd/sampling.hpp:7-32): the [-1,1) `offset` is computed and never used
+ * (the raw [0,1) samples are), the constants named pi_o_4 / pi_o_2 hold 4/pi and 2/pi, and simd::select(m, l, r)
+ * is blendv(l, r, m), i.e. m ? r : l (math/simd/float8.hpp:103-105) — so r and theta are taken from the
+ * "other" branch.  Pinned against the compiled reference kernel in tests/test_oracle_pin.py. */
+typedef struct { const float* m; float zoom, stepx, stepy, ratio, focal_distance, aperture_radius; } cam1;
+static void camera_ray1(const cam1* c, uint32_t px, uint32_t py, float jx, float jy, float lu, float lv, int rcp_mode, v3* o, v3* w) {
+  const float* m = c->m;
+  const float sy = (float)py, sx = (float)px;
+  const float ndcy = 0.5f - (-0.5f + sy) * c->stepy;
+  const float ndcx = (-0.5f + sx) * c->stepx - 0.5f;
+  v3 dd = V((ndcx + jx * c->stepx) * c->ratio * c->zoom, (ndcy + jy * c->stepy) * c->zoom, -1.0f);
+  dd = simd_normalize(dd, rcp_mode);
+  v3 p = V(0.0f, 0.0f, 0.0f);
+  if (c->aperture_radius != 0.0f) {
+    const float pi_o_2 = (float)(2.0f / M_PI), pi_o_4 = (float)(4.0f / M_PI);
+    const int x_gt_y = fabsf(lu) > fabsf(lv);
+    const float r = x_gt_y ? lv : lu;
+    const float theta1 = pi_o_4 * (lv / lu);
+    const float theta2 = pi_o_2 - pi_o_4 * (lu / lv);
+    const float theta = x_gt_y ? theta2 : theta1;
+    const float lx = (r * cosf(theta)) * c->aperture_radius, ly = (r * sinf(theta)) * c->aperture_radius;
+    const float ft = fabsf(c->focal_distance / dd.z);
+    p = V(lx, ly, 0.0f);
+    dd = V(dd.x * ft - p.x, dd.y * ft - p.y, dd.z * ft - p.z);
+    dd = simd_normalize(dd, rcp_mode);
+  }
+  /* transform_point / transform_vector (math/simd/matrix.hpp:58-104): mul, fmadd, fmadd, (+ row 3) */
+  *o = V(fmaf(p.z, m[8], fmaf(p.y, m[4], p.x * m[0])) + m[12], fmaf(p.z, m[9], fmaf(p.y, m[5], p.x * m[1])) + m[13],
+         fmaf(p.z, m[10], fmaf(p.y, m[6], p.x * m[2])) + m[14]);
+  *w = V(fmaf(dd.z, m[8], fmaf(dd.y, m[4], dd.x * m[0])), fmaf(dd.z, m[9], fmaf(dd.y, m[5], dd.x * m[1])),
+         fmaf(dd.z, m[10], fmaf(dd.y, m[6], dd.x * m[2])));
+}
+
+/* camera rays of a rectangle with caller-chosen samples (parity hook for the thin lens; slot = y * w + x) */
+void orc_camera_rays_lens(const phos_camera* cam, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, float jx, float jy,
+                          const float* lens_u, const float* lens_v, int rcp_mode, float* px, float* py, float* pz,
+                          float* wx, float* wy, float* wz) {
+  const cam1 c = {cam->to_world, 1.12f * tanf(cam->fov * 0.5f), 1.0f / (float)cam->film_width, 1.0f / (float)cam->film_height,
+                  (float)cam->film_width / (float)cam->film_height, cam->focal_distance, cam->aperture_radius};
+  for (uint32_t y = 0; y < h; ++y)
+    for (uint32_t x = 0; x < w; ++x) {
+      const size_t k = (size_t)y * w + x;
+      v3 o, d;
+      camera_ray1(&c, x0 + x, y0 + y, jx, jy, lens_u ? lens_u[k] : 0.5f, lens_v ? lens_v[k] : 0.5f, rcp_mode, &o, &d);
+      px[k] = o.x; py[k] = o.y; pz[k] = o.z;
+      wx[k] = d.x; wy[k] = d.y; wz[k] = d.z;
+    }
+}
+
 /* one ray through the oracle traversal */
 typedef struct { v3 o, w; float d; uint32_t mesh, face; float u, v; uint32_t flags; } ray1;
 static void trace1(const void* nodes, const void* packets, ray1* r, int rcp_mode) {
@@ -354,7 +406,7 @@ static void trace1(const void* nodes, const void* packets, ray1* r, int rcp_mode
  * radiance / (spp_total * pps) into film (W*H*4 floats, interleaved RGBA; alpha is set to 1). */
 void orc_render(void* scene_h, const void* nodes, const void* packets, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h,
                 uint32_t spp_begin, uint32_t spp_end, uint32_t spp_total, uint32_t pps, uint32_t max_depth, uint64_t seed64,
-                int rcp_mode, float* film) {
+                int rcp_mode, float* film, float* normals /* W*H*3 or NULL: the NORMALS channel, cpu.cpp:194-196 */) {
   const orc_scene* S = (const orc_scene*)scene_h;
   const phos_scene_desc* d = S->d;
   const uint32_t seed = (uint32_t)(seed64 ^ (seed64 >> 32));
@@ -362,9 +414,9 @@ void orc_render(void* scene_h, const void* nodes, const void* packets, uint32_t 
   float* jx = (float*)malloc(sizeof(float) * spp_total);
   float* jy = (float*)malloc(sizeof(float) * spp_total);
   orc_film_jitter(seed, spp_total, jx, jy);
-  const float* m = d->camera.to_world;
-  const float zoom = 1.12f * tanf(d->camera.fov * 0.5f);
-  const float stepx = 1.0f / (float)W, stepy = 1.0f / (float)H, ratio = (float)W / (float)H;
+  const cam1 cam = {d->camera.to_world, 1.12f * tanf(d->camera.fov * 0.5f), 1.0f / (float)W, 1.0f / (float)H, (float)W / (float)H,
+                    d->camera.focal_distance, d->camera.aperture_radius};
+  const int thin = d->camera.aperture_radius != 0.0f;
   const float scale = 1.0f / (spp_total * pps);
   const uint32_t nl = S->nlights;
 
@@ -377,15 +429,9 @@ void orc_render(void* scene_h, const void* nodes, const void* packets, uint32_t 
         /* camera ray: camera.hpp:113-152 (see orc_camera_rays in phos_oracle.c) */
         ray1 r;
         {
-          const float sy = (float)py, sx = (float)px;
-          const float ndcy = 0.5f - (-0.5f + sy) * stepy;
-          const float ndcx = (-0.5f + sx) * stepx - 0.5f;
-          v3 dd = V((ndcx + jx[s] * stepx) * ratio * zoom, (ndcy + jy[s] * stepy) * zoom, -1.0f);
-          dd = simd_normalize(dd, rcp_mode);
-          r.o = V(fmaf(0.0f, m[8], fmaf(0.0f, m[4], 0.0f * m[0])) + m[12], fmaf(0.0f, m[9], fmaf(0.0f, m[5], 0.0f * m[1])) + m[13],
-                  fmaf(0.0f, m[10], fmaf(0.0f, m[6], 0.0f * m[2])) + m[14]);
-          r.w = V(fmaf(dd.z, m[8], fmaf(dd.y, m[4], dd.x * m[0])), fmaf(dd.z, m[9], fmaf(dd.y, m[5], dd.x * m[1])),
-                  fmaf(dd.z, m[10], fmaf(dd.y, m[6], dd.x * m[2])));
+          /* lens sample: the reference draws two fresh uniforms per slot and sample (sampling.cpp:104-109) */
+          const float lu = thin ? orc_rnd(seed, pixel, s, 0, DIM_LENS) : 0.5f, lv = thin ? orc_rnd(seed, pixel, s, 1, DIM_LENS) : 0.5f;
+          camera_ray1(&cam, px, py, jx[s], jy[s], lu, lv, rcp_mode, &r.o, &r.w);
           r.d = FLT_MAX; r.flags = 0; r.mesh = r.face = 0; r.u = r.v = 0;
         }
         v3 beta = V(1, 1, 1), rad = V(0, 0, 0);
@@ -398,6 +444,9 @@ void orc_render(void* scene_h, const void* nodes, const void* packets, uint32_t 
           const v3 wo = neg(r.w);
           const uint32_t mesh = r.mesh & 0xffffu, mat = r.mesh >> 16;
           const v3 n = shading_normal(d, mesh, r.face, r.u, r.v);
+          if (depth == 0 && normals) { /* channels.normals->set(x, y, primary->n): the last sample that hits wins */
+            normals[3 * (size_t)pixel] = n.x; normals[3 * (size_t)pixel + 1] = n.y; normals[3 * (size_t)pixel + 2] = n.z;
+          }
           const phos_material* mt = &d->materials[mat];
           const v3 e = mt->kind == PHOS_MAT_EMITTER ? S->emission[mat] : V(0, 0, 0);
           /* NEE: fresh_light_samples (sampling.cpp:160-180) + light_sampler_t (spt.hpp:116-148) */

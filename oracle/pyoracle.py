@@ -50,10 +50,11 @@ class Oracle:
         L.orc_scene_destroy.argtypes = [C.c_void_p]
         L.orc_scene_num_lights.argtypes = [C.c_void_p]
         L.orc_scene_num_lights.restype = C.c_uint32
-        L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_uint32] * 9 + [C.c_uint64, C.c_int, C.c_void_p]
+        L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_uint32] * 9 + [C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_rnd.restype = C.c_float
         L.orc_rnd.argtypes = [C.c_uint32] * 5
         L.orc_film_jitter.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_camera_rays_lens.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
 
     def brute_force(self, packets: np.ndarray, rays: RayBatch) -> RayBatch:
         out = rays.copy()
@@ -79,8 +80,10 @@ class Oracle:
 
 
     def render(self, scene: Scene, nodes: np.ndarray, packets: np.ndarray, spp: int, pps: int = 1, depth: int = 9,
-               seed: int = 0, region=None, spp_range=None, rcp_mode: bool = False, film: np.ndarray | None = None):
-        """Scalar path tracer over a pixel rectangle (default: whole film); returns the RGBA film."""
+               seed: int = 0, region=None, spp_range=None, rcp_mode: bool = False, film: np.ndarray | None = None,
+               normals: np.ndarray | None = None):
+        """Scalar path tracer over a pixel rectangle (default: whole film); returns the RGBA film.  `normals`
+        (H, W, 3 float32) receives the NORMALS channel (cpu.cpp:194-196) when given."""
         cam = scene.camera
         d = scene.desc()
         h = self.lib.orc_scene_create(C.byref(d))
@@ -89,9 +92,22 @@ class Oracle:
         x0, y0, w, hh = region if region is not None else (0, 0, cam.film_width, cam.film_height)
         s0, s1 = spp_range if spp_range is not None else (0, spp)
         self.lib.orc_render(h, nodes.ctypes.data, packets.ctypes.data, x0, y0, w, hh, s0, s1, spp, pps, depth, seed,
-                            1 if rcp_mode else 0, film.ctypes.data)
+                            1 if rcp_mode else 0, film.ctypes.data, normals.ctypes.data if normals is not None else None)
         self.lib.orc_scene_destroy(h)
         return film
+
+    def camera_rays_lens(self, scene: Scene, x0, y0, w, h, jx, jy, lens_u, lens_v, rcp_mode: bool = False):
+        """camera::perspective_kernel_t for the rectangle with one film jitter and one lens sample per slot
+        (thin lens when scene.camera.aperture_radius != 0).  Returns (p, wi) as two (n, 3) float32 arrays."""
+        d = scene.desc()
+        n = w * h
+        out = [np.zeros(n, np.float32) for _ in range(6)]
+        lu = np.ascontiguousarray(lens_u, np.float32)
+        lv = np.ascontiguousarray(lens_v, np.float32)
+        cam_ptr = C.addressof(d) + type(d).camera.offset
+        self.lib.orc_camera_rays_lens(cam_ptr, x0, y0, w, h, jx, jy, lu.ctypes.data, lv.ctypes.data, 1 if rcp_mode else 0,
+                                      *[a.ctypes.data for a in out])
+        return np.stack(out[:3], 1), np.stack(out[3:], 1)
 
     def film_jitter(self, seed: int, spp: int):
         jx, jy = np.zeros(spp, np.float32), np.zeros(spp, np.float32)
@@ -127,10 +143,15 @@ class RefScene:
         secs = self.lib.ref_trace(self.h, 0 if kind == "stream" else 1, f, u, out.n, threads)
         return out, secs
 
-    def render(self, spp: int, pps: int = 1, depth: int = 9, single_threaded: bool = True):
+    def render(self, spp: int, pps: int = 1, depth: int = 9, single_threaded: bool = True, normals: np.ndarray | None = None,
+               cuda: bool = False):
+        """cpu_t (or, cuda=True, the drop-in cuda_t) start / join; `normals` (H, W, 3) requests the NORMALS channel."""
         cam = self._scene.camera
         img = np.zeros((cam.film_height, cam.film_width, 4), np.float32)
-        secs = self.lib.ref_render(self.h, spp, pps, depth, 1 if single_threaded else 0, img.ctypes.data)
+        secs = self.lib.ref_render_aov(self.h, spp, pps, depth, 1 if single_threaded else 0, 1 if cuda else 0, img.ctypes.data,
+                                       normals.ctypes.data if normals is not None else None)
+        if secs < 0:
+            raise RuntimeError("device raised (see stderr)")
         return img, secs
 
     def render_cuda(self, spp: int, pps: int = 1, depth: int = 9):
@@ -142,6 +163,16 @@ class RefScene:
         if secs < 0:
             raise RuntimeError("cuda_t raised (see stderr)")
         return img, secs
+
+    def camera_rays(self, x0, y0, w, h, jx, jy, lens_u, lens_v):
+        """The reference's own camera::perspective_kernel_t on one tile (w % 8 == 0, w * h <= 1024)."""
+        n = w * h
+        assert w % 8 == 0 and n <= 1024
+        out = [np.zeros(n, np.float32) for _ in range(6)]
+        lu = np.ascontiguousarray(lens_u, np.float32)
+        lv = np.ascontiguousarray(lens_v, np.float32)
+        self.lib.ref_camera_rays(self.h, x0, y0, w, h, jx, jy, lu.ctypes.data, lv.ctypes.data, *[a.ctypes.data for a in out])
+        return np.stack(out[:3], 1), np.stack(out[3:], 1)
 
     def num_lights(self):
         return self.lib.ref_scene_num_lights(self.h)
@@ -178,6 +209,9 @@ class RefLib:
         L.ref_render.restype = C.c_double
         L.ref_render_on.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
         L.ref_render_on.restype = C.c_double
+        L.ref_render_aov.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_render_aov.restype = C.c_double
+        L.ref_camera_rays.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_float, C.c_float] + [C.c_void_p] * 8
         L.ref_cuda_device_count.restype = C.c_int
         L.ref_hardware_concurrency.restype = C.c_uint32
         L.ref_sizeof_node.restype = C.c_uint32

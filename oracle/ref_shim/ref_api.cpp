@@ -21,6 +21,8 @@
 #include "state.hpp"
 #include "xpu/cpu.hpp"
 #include "xpu/cuda.hpp"
+// after scene.hpp: the kernel header uses camera_t without including entities/camera.hpp itself
+#include "kernels/cpu/camera.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -110,16 +112,24 @@ void store_stream(const ray_t<>* r, float* const* f, uint32_t* const* u, size_t 
 }
 
 struct memory_film_t : public film_t<> {
-  float* rgba;  // W*H*4, row-major
+  float* rgba;              // W*H*4, row-major
+  float* normals = nullptr; // W*H*3 when the NORMALS channel was requested
   uint32_t width, height;
   void add_tile(const Imath::V2i& pos, const Imath::V2i& size, const render_buffer_t& buffer) override {
     const auto* ch = buffer.channel(render_buffer_t::PRIMARY);
+    const auto* nc = normals ? buffer.channel(render_buffer_t::NORMALS) : nullptr;
     for (int y = 0; y < size.y; ++y)
       for (int x = 0; x < size.x; ++x) {
         float px[4] = {0, 0, 0, 0};
         ch->get(x, y, px);
         float* out = rgba + 4 * ((size_t)(pos.y + y) * width + (pos.x + x));
         out[0] = px[0]; out[1] = px[1]; out[2] = px[2]; out[3] = 1.0f;
+        if (nc) {
+          float n[4] = {0, 0, 0, 0};
+          nc->get(x, y, n);
+          float* o = normals + 3 * ((size_t)(pos.y + y) * width + (pos.x + x));
+          o[0] = n[0]; o[1] = n[1]; o[2] = n[2];
+        }
       }
   }
 };
@@ -240,6 +250,7 @@ double ref_trace(void* h, int kind, float* const* f, uint32_t* const* u, uint64_
 // Render a frame with the reference's own CPU device (cpu_t::preprocess/start/join) into an RGBA
 // float image.  Wall clock around start -> join like src/core.cpp:158-177.  Returns seconds.
 double ref_render_on(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, int use_cuda, float* rgba);
+double ref_render_aov(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, int use_cuda, float* rgba, float* normals);
 double ref_render(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, float* rgba) {
   return ref_render_on(h, spp, pps, depth, single_threaded, 0, rgba);
 }
@@ -248,6 +259,12 @@ double ref_render(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int singl
 // with exactly the calls session_t::details_t::render makes (plugins/blender/session.cpp:73-94).
 // Returns seconds, or -1 with a message on stderr if the device raised.
 double ref_render_on(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, int use_cuda, float* rgba) {
+  return ref_render_aov(h, spp, pps, depth, single_threaded, use_cuda, rgba, nullptr);
+}
+
+// ... and with the NORMALS channel (render_buffer_t::NORMALS, src/xpu/cpu.cpp:97,194-196) when `normals` is given
+double ref_render_aov(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int single_threaded, int use_cuda, float* rgba,
+                      float* normals) {
   auto* s = static_cast<ref_scene*>(h);
   parsed_options_t options;
   options.samples_per_pixel = spp;
@@ -259,6 +276,7 @@ double ref_render_on(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int si
   const uint32_t W = s->scene.camera.film.width, H = s->scene.camera.film.height;
   render_buffer_t::descriptor_t format;
   format.request(render_buffer_t::PRIMARY, 4);
+  if (normals) format.request(render_buffer_t::NORMALS, 3);
 
   xpu_t* device = nullptr;
   try {
@@ -273,6 +291,7 @@ double ref_render_on(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int si
   job::tiles_t* tiles = job::tiles_t::make(W, H, 32, format);
   memory_film_t film;
   film.rgba = rgba;
+  film.normals = normals;
   film.width = W;
   film.height = H;
   sampler_t* sampler = new sampler_t(options);
@@ -294,4 +313,36 @@ int ref_cuda_device_count(void) { return cuda_t::device_count(); }
 
 uint32_t ref_hardware_concurrency(void) { return std::thread::hardware_concurrency(); }
 
+
+// camera::perspective_kernel_t (src/kernels/cpu/camera.hpp:78-159) on one tile with caller-chosen samples:
+// one film jitter for the whole tile, one lens sample per slot (slot = y * tile.w + x; tile.w % 8 == 0,
+// tile.w * tile.h <= 1024).  Writes p / wi of the tile's slots.
+void ref_camera_rays(ref_scene* s, uint32_t tx, uint32_t ty, uint32_t tw, uint32_t th, float jx, float jy,
+                     const float* lens_x, const float* lens_y, float* px, float* py, float* pz, float* wx, float* wy,
+                     float* wz) {
+  struct tile_t { uint32_t x, y, w, h; } tile = {tx, ty, tw, th};
+  sampler_t::pixel_samples_t* samples;
+  posix_memalign((void**)&samples, 32, sizeof(sampler_t::pixel_samples_t));
+  const uint32_t n = tw * th;
+  for (uint32_t j = 0; j < 128; ++j)
+    for (uint32_t k = 0; k < 8; ++k) {
+      samples->film[j].x[k] = jx;
+      samples->film[j].y[k] = jy;
+      const uint32_t slot = j * 8 + k;
+      samples->lens[j].x[k] = slot < n ? lens_x[slot] : 0.5f;
+      samples->lens[j].y[k] = slot < n ? lens_y[slot] : 0.5f;
+    }
+  ray_t<>* rays;
+  posix_memalign((void**)&rays, 32, sizeof(ray_t<>));
+  camera::perspective_kernel_t kernel;
+  kernel(s->scene.camera, tile, *samples, rays);
+  memcpy(px, rays->p.x, n * 4);
+  memcpy(py, rays->p.y, n * 4);
+  memcpy(pz, rays->p.z, n * 4);
+  memcpy(wx, rays->wi.x, n * 4);
+  memcpy(wy, rays->wi.y, n * 4);
+  memcpy(wz, rays->wi.z, n * 4);
+  free(rays);
+  free(samples);
+}
 }  // extern "C"

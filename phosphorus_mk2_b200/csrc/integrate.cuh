@@ -58,7 +58,7 @@ __host__ __device__ __forceinline__ float rng(uint32_t seed, uint32_t pixel, uin
   h = rng_mix(h ^ (0xC2B2AE35u * (bounce * 8u + dim + 1u)));
   return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
-enum { DIM_LIGHT = 0, DIM_LIGHT_U = 1, DIM_LIGHT_V = 2, DIM_BSDF_U = 3, DIM_BSDF_V = 4, DIM_RR = 5, DIM_FILM = 7 };
+enum { DIM_LIGHT = 0, DIM_LIGHT_U = 1, DIM_LIGHT_V = 2, DIM_BSDF_U = 3, DIM_BSDF_V = 4, DIM_RR = 5, DIM_LENS = 6, DIM_FILM = 7 };
 
 // ---- scene tables in HBM -------------------------------------------------------------------------------
 struct DevMaterial {

@@ -29,35 +29,18 @@ void phos_render_release(phos_ctx* ctx) {
 // One deliberate difference: normalize() multiplies by _mm256_rcp_ps(sqrt(l)) in the reference
 // (~12-bit, micro-architecture specific, src/math/simd/vector.hpp:126-133); here it is the correctly
 // rounded 1/sqrt(l).
-__device__ __forceinline__ void camera_ray(const DevCamera& cam, uint32_t px, uint32_t py, float jx, float jy, float* o,
-                                           float* w) {
-  const float sx = (float)px, sy = (float)py;
-  const float ndcy = __fsub_rn(0.5f, __fmul_rn(__fadd_rn(-0.5f, sy), cam.stepy));
-  const float ndcx = __fsub_rn(__fmul_rn(__fadd_rn(-0.5f, sx), cam.stepx), 0.5f);
-  float dx = __fmul_rn(__fmul_rn(__fadd_rn(ndcx, __fmul_rn(jx, cam.stepx)), cam.ratio), cam.zoom);
-  float dy = __fmul_rn(__fadd_rn(ndcy, __fmul_rn(jy, cam.stepy)), cam.zoom);
-  float dz = -1.0f;
-  const float l = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
-  const float ool = __fdiv_rn(1.0f, __fsqrt_rn(l));
-  dx = __fmul_rn(dx, ool);
-  dy = __fmul_rn(dy, ool);
-  dz = __fmul_rn(dz, ool);
-  const float* m = cam.m;
-  o[0] = __fadd_rn(__fmaf_rn(0.0f, m[8], __fmaf_rn(0.0f, m[4], __fmul_rn(0.0f, m[0]))), m[12]);
-  o[1] = __fadd_rn(__fmaf_rn(0.0f, m[9], __fmaf_rn(0.0f, m[5], __fmul_rn(0.0f, m[1]))), m[13]);
-  o[2] = __fadd_rn(__fmaf_rn(0.0f, m[10], __fmaf_rn(0.0f, m[6], __fmul_rn(0.0f, m[2]))), m[14]);
-  w[0] = __fmaf_rn(dz, m[8], __fmaf_rn(dy, m[4], __fmul_rn(dx, m[0])));
-  w[1] = __fmaf_rn(dz, m[9], __fmaf_rn(dy, m[5], __fmul_rn(dx, m[1])));
-  w[2] = __fmaf_rn(dz, m[10], __fmaf_rn(dy, m[6], __fmul_rn(dx, m[2])));
-}
-
 __global__ void camera_rays_kernel(const DevCamera cam, const phos_tile* __restrict__ tiles,
-                                   const unsigned long long* __restrict__ offsets, float jx, float jy, phos_rays out) {
+                                   const unsigned long long* __restrict__ offsets, float jx, float jy, uint32_t seed,
+                                   uint32_t sample, phos_rays out) {
   const phos_tile t = tiles[blockIdx.y];
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= t.w * t.h) return;
   float o[3], w[3];
-  camera_ray(cam, t.x + k % t.w, t.y + k / t.w, jx, jy, o, w);
+  const uint32_t px = t.x + k % t.w, py = t.y + k / t.w, pix = py * cam.width + px;
+  // lens sample of (pixel, sample): the same two draws the wavefront takes (wavefront.cu paths_init_kernel)
+  const bool thin = cam.aperture_radius != 0.0f;
+  const float lu = thin ? rng(seed, pix, sample, 0, DIM_LENS) : 0.5f, lv = thin ? rng(seed, pix, sample, 1, DIM_LENS) : 0.5f;
+  camera_ray(cam, px, py, jx, jy, lu, lv, o, w);
   const unsigned long long i = offsets[blockIdx.y] + k;
   out.px[i] = o[0];
   out.py[i] = o[1];
@@ -76,6 +59,8 @@ DevCamera make_camera(const phos_camera& c) {
   d.stepx = 1.0f / (float)c.film_width;
   d.stepy = 1.0f / (float)c.film_height;
   d.ratio = (float)c.film_width / (float)c.film_height;
+  d.focal_distance = c.focal_distance;
+  d.aperture_radius = c.aperture_radius;
   d.width = c.film_width;
   d.height = c.film_height;
   return d;
@@ -101,6 +86,11 @@ int phos_cuda_upload_scene(phos_ctx* ctx, const phos_scene_desc* scene) {
 
 int phos_cuda_camera_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, float jx, float jy,
                           const phos_rays* device_rays) {
+  return phos_cuda_camera_rays_lens(ctx, tiles, n_tiles, jx, jy, 0, 0, device_rays);
+}
+
+int phos_cuda_camera_rays_lens(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, float jx, float jy, uint64_t seed64,
+                               uint32_t sample, const phos_rays* device_rays) {
   if (!ctx || !tiles || !device_rays) return PHOS_ERR_INVALID;
   if (!ctx->render) return fail(ctx, PHOS_ERR_INVALID, "camera_rays before upload_scene");
   if (n_tiles == 0) return PHOS_OK;
@@ -123,7 +113,7 @@ int phos_cuda_camera_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tile
     const uint32_t cnt = std::min<uint32_t>(65535, n_tiles - first);
     dim3 grid((max_px + block - 1) / block, cnt);
     camera_rays_kernel<<<grid, block, 0, ctx->stream>>>(R.camera, R.d_tiles + first, R.d_tile_offsets + first, jx, jy,
-                                                        *device_rays);
+                                                        (uint32_t)(seed64 ^ (seed64 >> 32)), sample, *device_rays);
     ctx->launches++;
   }
   return cuda_ok(ctx, cudaGetLastError(), "camera_rays_kernel launch") ? PHOS_OK : PHOS_ERR_CUDA;
@@ -306,6 +296,8 @@ void RenderState::release() {
   for (void* p : scene_allocs) cudaFree(p);
   scene_allocs.clear();
   if (film) cudaFree(film);
+  if (film_normals) cudaFree(film_normals);
+  film_normals = nullptr;
   if (d_jitter) cudaFree(d_jitter);
   film = nullptr;
   d_jitter = nullptr;

@@ -6,19 +6,14 @@
 #include <vector>
 
 #include "../../include/phos_cuda.h"
+#include "camera.cuh"
 #include "ctx.hpp"
 #include "integrate.cuh"
 
 namespace phos {
 
-// camera_t (reference src/entities/camera.hpp:10-40) with the per-frame constants of
+// DevCamera (camera.cuh): camera_t (reference src/entities/camera.hpp:10-40) with the per-frame constants of
 // camera::perspective_kernel_t hoisted (src/kernels/cpu/camera.hpp:113-122)
-struct DevCamera {
-  float m[16];  // to_world, row-vector convention
-  float zoom;   // 1.12 * tan(fov / 2)
-  float stepx, stepy, ratio;
-  uint32_t width, height;
-};
 
 // Wavefront state for up to `capacity` concurrent paths (SoA, all in HBM).
 struct Wavefront {
@@ -47,6 +42,7 @@ struct RenderState {
   uint32_t num_meshes = 0, num_materials = 0;
 
   float* film = nullptr;  // W * H * 4
+  float* film_normals = nullptr;  // W * H * 3, the NORMALS channel (allocated by phos_cuda_enable_normals)
   float* d_jitter = nullptr;
   uint32_t jitter_capacity = 0;
   Wavefront wf;

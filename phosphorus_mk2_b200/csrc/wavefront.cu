@@ -26,29 +26,6 @@
 
 namespace phos {
 
-__device__ __forceinline__ void camera_ray_exact(const DevCamera& cam, uint32_t px, uint32_t py, float jx, float jy, float* o,
-                                                 float* w) {
-  // same arithmetic as camera_rays_kernel (render.cu); see the comment there
-  const float sx = (float)px, sy = (float)py;
-  const float ndcy = __fsub_rn(0.5f, __fmul_rn(__fadd_rn(-0.5f, sy), cam.stepy));
-  const float ndcx = __fsub_rn(__fmul_rn(__fadd_rn(-0.5f, sx), cam.stepx), 0.5f);
-  float dx = __fmul_rn(__fmul_rn(__fadd_rn(ndcx, __fmul_rn(jx, cam.stepx)), cam.ratio), cam.zoom);
-  float dy = __fmul_rn(__fadd_rn(ndcy, __fmul_rn(jy, cam.stepy)), cam.zoom);
-  float dz = -1.0f;
-  const float l = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
-  const float ool = __fdiv_rn(1.0f, __fsqrt_rn(l));
-  dx = __fmul_rn(dx, ool);
-  dy = __fmul_rn(dy, ool);
-  dz = __fmul_rn(dz, ool);
-  const float* m = cam.m;
-  o[0] = __fadd_rn(__fmaf_rn(0.0f, m[8], __fmaf_rn(0.0f, m[4], __fmul_rn(0.0f, m[0]))), m[12]);
-  o[1] = __fadd_rn(__fmaf_rn(0.0f, m[9], __fmaf_rn(0.0f, m[5], __fmul_rn(0.0f, m[1]))), m[13]);
-  o[2] = __fadd_rn(__fmaf_rn(0.0f, m[10], __fmaf_rn(0.0f, m[6], __fmul_rn(0.0f, m[2]))), m[14]);
-  w[0] = __fmaf_rn(dz, m[8], __fmaf_rn(dy, m[4], __fmul_rn(dx, m[0])));
-  w[1] = __fmaf_rn(dz, m[9], __fmaf_rn(dy, m[5], __fmul_rn(dx, m[1])));
-  w[2] = __fmaf_rn(dz, m[10], __fmaf_rn(dy, m[6], __fmul_rn(dx, m[2])));
-}
-
 struct FrameArgs {
   DevCamera cam;
   DevScene scene;
@@ -87,7 +64,10 @@ __global__ void paths_init_kernel(const FrameArgs A, phos_rays rays, uint32_t* _
   if (q >= A.Q) return;
   const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P];
   float o[3], w[3];
-  camera_ray_exact(A.cam, pix % A.cam.width, pix / A.cam.width, A.jitter[2 * s], A.jitter[2 * s + 1], o, w);
+  // lens sample: the reference draws two fresh uniforms per slot and sample (sampling.cpp:104-109)
+  const bool thin = A.cam.aperture_radius != 0.0f;
+  const float lu = thin ? rng(A.seed, pix, s, 0, DIM_LENS) : 0.5f, lv = thin ? rng(A.seed, pix, s, 1, DIM_LENS) : 0.5f;
+  camera_ray(A.cam, pix % A.cam.width, pix / A.cam.width, A.jitter[2 * s], A.jitter[2 * s + 1], lu, lv, o, w);
   rays.px[q] = o[0];
   rays.py[q] = o[1];
   rays.pz[q] = o[2];
@@ -293,6 +273,23 @@ __global__ void film_accumulate_kernel(const FrameArgs A, float* __restrict__ fi
   px[3] = 1.0f;
 }
 
+// render_buffer_t::NORMALS (cpu.cpp:97,194-196): channels.normals->set(x, y, primary->n) after every sample
+// whose primary ray hit, samples in order — so a pixel ends up with the shading normal of its LAST sample
+// that hit.  Runs after the first shade_nee of a sample batch (slot = path = tile pixel + sample * P there).
+__global__ void normals_channel_kernel(const FrameArgs A, const phos_rays rays, uint32_t samples, float* __restrict__ film_n) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.P) return;
+  for (uint32_t s = samples; s-- > 0;) {
+    const size_t q = t + (size_t)s * A.P;
+    if (!(rays.flags[q] & PHOS_HIT)) continue;
+    float* o = film_n + 3 * (size_t)A.pixel[t];
+    o[0] = A.n[q];
+    o[1] = A.n[q + (size_t)A.Q];
+    o[2] = A.n[q + 2 * (size_t)A.Q];
+    return;
+  }
+}
+
 __global__ void zero_u32_kernel(uint32_t* p) { *p = 0u; }
 
 // sample::stratified_2d (math/sampling.hpp:67-82) as sampler_t::preprocess uses it (sampling.cpp:96-99):
@@ -408,6 +405,10 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
       if (rc) return rc;
       shade_nee_kernel<<<blocks, 256, 0, st>>>(A, W.rays[cur], W.slot_path[cur], cur, W.shadow);
       ctx->launches++;
+      if (b == 0 && R.film_normals) {
+        normals_channel_kernel<<<(P + 255) / 256, 256, 0, st>>>(A, W.rays[0], ns, R.film_normals);
+        ctx->launches++;
+      }
       rc = launch_trace(ctx, W.shadow, A.Q, st, ctx->d_counters + 25, false, W.count + cur);
       if (rc) return rc;
       integrate_kernel<<<blocks, 256, 0, st>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1]);
@@ -514,6 +515,37 @@ int phos_cuda_film_device_ptr(phos_ctx* ctx, void** out_ptr, uint64_t* out_float
   if (!ctx || !ctx->render || !ctx->render->film || !out_ptr) return PHOS_ERR_INVALID;
   *out_ptr = ctx->render->film;
   if (out_floats) *out_floats = (uint64_t)ctx->render->camera.width * ctx->render->camera.height * 4;
+  return PHOS_OK;
+}
+
+int phos_cuda_enable_normals(phos_ctx* ctx, int on) {
+  if (!ctx || !ctx->render || !ctx->render->film) return fail(ctx, PHOS_ERR_INVALID, "enable_normals before upload_scene");
+  cudaSetDevice(ctx->device);
+  RenderState& R = *ctx->render;
+  cudaStreamSynchronize(ctx->stream);
+  if (!on) {
+    if (R.film_normals) cudaFree(R.film_normals);
+    R.film_normals = nullptr;
+    return PHOS_OK;
+  }
+  const size_t bytes = (size_t)R.camera.width * R.camera.height * 3 * sizeof(float);
+  if (!R.film_normals && !cuda_ok(ctx, cudaMalloc(&R.film_normals, bytes), "cudaMalloc(normals channel)")) return PHOS_ERR_CUDA;
+  return cuda_ok(ctx, cudaMemset(R.film_normals, 0, bytes), "clear normals channel") ? PHOS_OK : PHOS_ERR_CUDA;
+}
+
+int phos_cuda_film_read_normals(phos_ctx* ctx, float* xyz, uint32_t x, uint32_t y, uint32_t w, uint32_t h) {
+  if (!ctx || !ctx->render || !xyz) return PHOS_ERR_INVALID;
+  if (!ctx->render->film_normals) return fail(ctx, PHOS_ERR_INVALID, "normals channel not enabled");
+  const DevCamera& c = ctx->render->camera;
+  if (x + w > c.width || y + h > c.height) return fail(ctx, PHOS_ERR_INVALID, "rectangle outside the film");
+  if (w == 0 || h == 0) return PHOS_OK;
+  cudaSetDevice(ctx->device);
+  const float* src = ctx->render->film_normals + 3 * ((size_t)y * c.width + x);
+  if (!cuda_ok(ctx,
+               cudaMemcpy2DAsync(xyz, (size_t)w * 12, src, (size_t)c.width * 12, (size_t)w * 12, h, cudaMemcpyDeviceToHost, ctx->stream),
+               "film_read_normals") ||
+      !cuda_ok(ctx, cudaStreamSynchronize(ctx->stream), "film_read_normals sync"))
+    return PHOS_ERR_CUDA;
   return PHOS_OK;
 }
 

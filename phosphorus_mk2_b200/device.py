@@ -185,11 +185,12 @@ class CudaDevice:
         self._check(self._L.phos_cuda_upload_scene(self._ctx, C.byref(d)))
         self._film_wh = (scene.camera.film_width, scene.camera.film_height)
 
-    def camera_rays(self, tiles, rays: DeviceRays, jx: float = 0.5, jy: float = 0.5) -> None:
-        """camera::perspective_kernel_t over a list of (x, y, w, h) tiles into a device stream."""
+    def camera_rays(self, tiles, rays: DeviceRays, jx: float = 0.5, jy: float = 0.5, seed: int = 0, sample: int = 0) -> None:
+        """camera::perspective_kernel_t over a list of (x, y, w, h) tiles into a device stream; with a thin-lens
+        camera the lens samples are the renderer's draws for (seed, pixel, sample)."""
         arr = tile_array(tiles)
         assert sum(t[2] * t[3] for t in tiles) <= rays.n
-        self._check(self._L.phos_cuda_camera_rays(self._ctx, arr, len(tiles), jx, jy, C.byref(rays.s)))
+        self._check(self._L.phos_cuda_camera_rays_lens(self._ctx, arr, len(tiles), jx, jy, seed, sample, C.byref(rays.s)))
 
     def render(self, tiles, spp_begin: int, spp_end: int, spp_total: int, seed: int = 0) -> None:
         """tile_renderer_t::render_tile over a tile list (src/xpu/cpu.cpp:156-205): accumulate samples
@@ -216,6 +217,17 @@ class CudaDevice:
         h = self._film_wh[1] - y if h is None else h
         out = np.zeros((h, w, 4), np.float32)
         self._check(self._L.phos_cuda_film_read(self._ctx, out.ctypes.data, x, y, w, h))
+        return out
+
+    def enable_normals(self, on: bool = True) -> None:
+        """Request the NORMALS channel (render_buffer_t::NORMALS, cpu.cpp:97,194-196) for the following renders."""
+        self._check(self._L.phos_cuda_enable_normals(self._ctx, 1 if on else 0))
+
+    def film_read_normals(self, x: int = 0, y: int = 0, w: int | None = None, h: int | None = None) -> np.ndarray:
+        w = self._film_wh[0] - x if w is None else w
+        h = self._film_wh[1] - y if h is None else h
+        out = np.zeros((h, w, 3), np.float32)
+        self._check(self._L.phos_cuda_film_read_normals(self._ctx, out.ctypes.data, x, y, w, h))
         return out
 
     def film_device_ptr(self) -> tuple[int, int]:

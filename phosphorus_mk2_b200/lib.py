@@ -73,11 +73,14 @@ SYMBOLS = {
     "phos_cuda_flush_l2": (_I, [_VP]),
     "phos_cuda_upload_scene": (_I, [_VP, C.POINTER(PhosSceneDesc)]),
     "phos_cuda_camera_rays": (_I, [_VP, C.POINTER(PhosTile), _U32, C.c_float, C.c_float, _RP]),
+    "phos_cuda_camera_rays_lens": (_I, [_VP, C.POINTER(PhosTile), _U32, C.c_float, C.c_float, C.c_uint64, _U32, _RP]),
     "phos_cuda_render": (_I, [_VP, C.POINTER(PhosTile), _U32, _U32, _U32, _U32, _U64]),
     "phos_cuda_wavefront_rays": (_I, [_VP, C.POINTER(PhosTile), _U32, _U32, _U32, _U64, _I, _RP, _U64, C.POINTER(_U64)]),
     "phos_cuda_film_clear": (_I, [_VP]),
     "phos_cuda_film_device_ptr": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U64)]),
     "phos_cuda_film_read": (_I, [_VP, _VP, _U32, _U32, _U32, _U32]),
+    "phos_cuda_enable_normals": (_I, [_VP, C.c_int]),
+    "phos_cuda_film_read_normals": (_I, [_VP, _VP, _U32, _U32, _U32, _U32]),
 }
 
 _libs: dict = {}

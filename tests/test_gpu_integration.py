@@ -42,3 +42,22 @@ def test_gpu_and_cpu_device_agree_statistically(reflib):
     cpu, _ = reflib.scene(sc).render(256, 1, 4, single_threaded=True)
     g, c = np.median(gpu[..., :3]), np.median(cpu[..., :3])
     assert 1.0 < g / c < 1.6
+
+
+def test_normals_channel_and_thin_lens_through_the_reference_host_code(reflib, oracle):
+    """The tile format asks for render_buffer_t::NORMALS and the camera has an aperture: cuda_t, driven by the
+    reference's tiles_t / film_t, hands back the same NORMALS channel the reference's cpu_t produces (up to
+    the different film jitter on silhouettes) and a depth-of-field image equal to the oracle's."""
+    sc = scenes.cornell_box(64, 64)
+    sc.camera.aperture_radius = 0.05
+    sc.camera.focal_distance = 3.3
+    rs = reflib.scene(sc)
+    gn = np.zeros((64, 64, 3), np.float32)
+    gimg, _ = rs.render(8, 1, 3, normals=gn, cuda=True)
+    cn = np.zeros_like(gn)
+    rs.render(8, 1, 3, normals=cn)
+    assert (np.abs(gn - cn).max(axis=2) < 2e-3).mean() > 0.9
+    acc = Accel(sc)
+    want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), 8, 1, 3, seed=0)
+    err = float(np.abs(gimg[..., :3] - want[..., :3]).mean() / np.abs(want[..., :3]).mean())
+    assert err < 1e-3

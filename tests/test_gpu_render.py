@@ -47,6 +47,70 @@ def test_cornell_image_matches_oracle(oracle, kind, depth, spp):
     assert np.all(got[..., 3] == 1.0)
 
 
+def test_thin_lens_camera(oracle):
+    """camera_t with aperture_radius != 0 (kernels/cpu/camera.hpp:140-147): primary rays against the oracle's
+    restatement (itself pinned bit for bit to the compiled reference kernel) on the renderer's own lens draws,
+    then the depth-of-field image at matched samples."""
+    sc = scenes.cornell_box(64, 64)
+    sc.camera.aperture_radius = 0.08
+    sc.camera.focal_distance = 3.3
+    acc = Accel(sc)
+    dev = CudaDevice.make(Options(4, 1, 4), 0)
+    dev.preprocess(sc, acc)
+    dev.upload_scene(sc)
+    W = H = 64
+    dr = dev.device_rays(W * H)
+    seed, sample = 11, 2
+    dev.camera_rays([(0, 0, W, H)], dr, 0.25, 0.75, seed=seed, sample=sample)
+    got = dr.download()
+    dr.free()
+    dev.close()
+    s32 = (seed ^ (seed >> 32)) & 0xFFFFFFFF
+    pix = np.arange(W * H)
+    lu = np.array([oracle.lib.orc_rnd(s32, int(p), sample, 0, 6) for p in pix], np.float32)
+    lv = np.array([oracle.lib.orc_rnd(s32, int(p), sample, 1, 6) for p in pix], np.float32)
+    wp, ww = oracle.camera_rays_lens(sc, 0, 0, W, H, 0.25, 0.75, lu, lv)
+    gp = np.stack([got.px, got.py, got.pz], 1)
+    gw = np.stack([got.wx, got.wy, got.wz], 1)
+    assert np.abs(gp - wp).max() < 2e-6 and np.abs(gw - ww).max() < 2e-6  # CUDA vs glibc sinf / cosf
+    assert np.abs(gp - gp[0]).max() > 1e-2                                # origins spread over the lens
+    want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), 8, 1, 4, seed=21)
+    img, _ = render_gpu(sc, acc, 8, 4, 21)
+    assert mean_rel_err(img, want) < 1e-3
+    sc.camera.aperture_radius = 0.0
+    pin, _ = render_gpu(sc, acc, 8, 4, 21)
+    assert mean_rel_err(img, pin) > 1e-2  # and it is not the pinhole image
+
+
+def test_normals_channel(oracle):
+    """render_buffer_t::NORMALS: the shading normal of the last sample whose primary ray hit, against the oracle
+    (same film jitter, so bit-level agreement up to CUDA vs host normalisation), whole frame, several sample
+    batches, flat and smooth meshes, partial tiles."""
+    from phosphorus_mk2_b200.scene import MAT_EMITTER, Material, Mesh
+    spheres = scenes.sphere_field(2, 24, 12, 70, 50, smooth=True)
+    light = spheres.add_material(Material(MAT_EMITTER, (1.0, 0.9, 0.8), power=30.0))
+    v = np.array([[-1.5, 2.0, -1.5], [1.5, 2.0, -1.5], [1.5, 2.0, 1.5], [-1.5, 2.0, 1.5]], np.float32)
+    nrm = np.tile(np.array([[0, -1, 0]], np.float32), (4, 1))
+    spheres.add(Mesh(v, np.array([[0, 1, 2], [0, 2, 3]]), [(light, np.arange(2))], smooth=False, normals=nrm))
+    for sc in (scenes.cornell_box(64, 64), spheres):
+        acc = Accel(sc)
+        cam = sc.camera
+        want = np.zeros((cam.film_height, cam.film_width, 3), np.float32)
+        oracle.render(sc, acc.nodes_array(), acc.packets_array(), 6, 1, 2, seed=9, normals=want)
+        dev = CudaDevice.make(Options(6, 1, 2), 0)
+        dev.preprocess(sc, acc)
+        dev.upload_scene(sc)
+        dev.enable_normals()
+        tiles = make_tiles(cam.film_width, cam.film_height)
+        for (a, b) in ((0, 2), (2, 3), (3, 6)):
+            dev.render(tiles, a, b, 6, 9)
+        got = dev.film_read_normals()
+        dev.close()
+        assert np.abs(got - want).max() < 1e-5
+        hit = np.abs(want).sum(axis=2) > 0
+        assert 0.3 < hit.mean() and np.array_equal(hit, np.abs(got).sum(axis=2) > 0)
+
+
 def test_partial_tiles_and_smooth_normals(oracle):
     """Film 70 x 50 (partial tiles right and bottom), smooth-shaded spheres + an emissive quad."""
     sc = scenes.sphere_field(2, 24, 12, 70, 50, smooth=True)

@@ -66,3 +66,29 @@ def test_film_jitter_is_stratified(oracle):
     jx, jy = oracle.film_jitter(3, 16)
     cells = set((int(x * 4), int(y * 4)) for x, y in zip(jx, jy))
     assert len(cells) == 16 and jx.min() >= 0 and jx.max() < 1
+
+
+def test_normals_channel_matches_reference_renderer(oracle, reflib):
+    """render_buffer_t::NORMALS (cpu.cpp:194-196): the shading normal of the last sample whose primary ray hit.
+    Flat and smooth meshes; the two renderers jitter the film differently (mt19937 vs counter RNG), so pixels
+    on silhouettes may pick the neighbouring face and interpolated normals move with the hit point inside the
+    pixel: flat walls agree to rounding, smooth spheres to the normal's variation across one pixel."""
+    from phosphorus_mk2_b200.scene import MAT_EMITTER, Material, Mesh
+    spheres = scenes.sphere_field(2, 24, 12, 64, 48, smooth=True)  # partial tiles at the bottom
+    light = spheres.add_material(Material(MAT_EMITTER, (1.0, 0.9, 0.8), power=30.0))  # the reference needs >= 1 light
+    v = np.array([[-1.5, 2.0, -1.5], [1.5, 2.0, -1.5], [1.5, 2.0, 1.5], [-1.5, 2.0, 1.5]], np.float32)
+    nrm = np.tile(np.array([[0, -1, 0]], np.float32), (4, 1))
+    spheres.add(Mesh(v, np.array([[0, 1, 2], [0, 2, 3]]), [(light, np.arange(2))], smooth=False, normals=nrm))
+    for sc, tol in ((scenes.cornell_box(64, 64), 2e-3), (spheres, 0.08)):
+        rs = reflib.scene(sc)
+        rs.build()
+        nodes, packets = rs.accel()
+        cam = sc.camera
+        rn = np.zeros((cam.film_height, cam.film_width, 3), np.float32)
+        rs.render(4, 1, 2, normals=rn)
+        on = np.zeros_like(rn)
+        oracle.render(sc, nodes, packets, 4, 1, 2, seed=3, normals=on)
+        close = np.abs(rn - on).max(axis=2) < tol
+        assert close.mean() > 0.93, close.mean()
+        hit = np.abs(on).sum(axis=2) > 0
+        assert hit.mean() > 0.3 and np.allclose(np.linalg.norm(on[hit], axis=1), 1.0, atol=1e-5)
