@@ -75,7 +75,6 @@ extern "C" {
 int phos_cuda_upload_scene(phos_ctx* ctx, const phos_scene_desc* scene) {
   if (!ctx || !scene) return PHOS_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  if (scene->camera.aperture_radius != 0.0f) return fail(ctx, PHOS_ERR_INVALID, "thin-lens cameras are not supported (pinhole only)");
   if (scene->camera.film_width == 0 || scene->camera.film_height == 0) return fail(ctx, PHOS_ERR_INVALID, "empty film");
   cudaStreamSynchronize(ctx->stream);
   phos_render_release(ctx);
