@@ -21,16 +21,43 @@ extern "C" {
  * src/shaders/diffuse_bsdf_node.osl:20-25, glossy_bsdf_node.osl:26-34,
  * diffuse_emitter_node.osl:18). */
 enum {
-  PHOS_MAT_DIFFUSE = 0, /* Cs * diffuse(N)                                  */
-  PHOS_MAT_GLOSSY  = 1, /* Cs * microfacet("ggx", N, 0, r*r, r*r, 0, 0)     */
-  PHOS_MAT_EMITTER = 2  /* (power / pi) * Cs * emission()                   */
+  PHOS_MAT_DIFFUSE    = 0, /* diffuse_bsdf_node: Cs * diffuse(N), or Cs * oren_nayar(N, roughness) if roughness != 0 */
+  PHOS_MAT_GLOSSY     = 1, /* glossy_bsdf_node: Cs * microfacet("ggx", N, 0, r*r, r*r, 0, 0), or Cs * reflection(N, 0)
+                              if roughness == 0 (glossy_bsdf_node.osl:28-33)                                        */
+  PHOS_MAT_EMITTER    = 2, /* diffuse_emitter_node: (power / pi) * Cs * emission()                                  */
+  PHOS_MAT_BACKGROUND = 3, /* background_node: Cs * power * background() — only as phos_scene_desc.environment      */
+  PHOS_MAT_LAYERED    = 4  /* an explicit closure list (what mix_closure_node / add_node trees flatten to in
+                              material_t::details_t::eval_closure, src/material.cpp:218-305): lobes[0..num_lobes)   */
 };
 
+/* Closure ids = bsdf_t::type_t (src/bsdf.hpp:14-24).  `param`: oren_nayar sigma in degrees
+ * (bsdf/params.hpp:31-42), microfacet xalpha = yalpha BEFORE precompute (the glossy node passes roughness^2),
+ * reflection / refraction eta, sheen roughness; unused otherwise.  Microfacet is the GGX reflection lobe
+ * (refract = 0); the rough-refraction variant is not part of this subset. */
+enum {
+  PHOS_LOBE_DIFFUSE     = 1,
+  PHOS_LOBE_OREN_NAYAR  = 2,
+  PHOS_LOBE_REFLECTION  = 4,
+  PHOS_LOBE_REFRACTION  = 8,
+  PHOS_LOBE_MICROFACET  = 16,
+  PHOS_LOBE_SHEEN       = 32,
+  PHOS_LOBE_TRANSPARENT = 128
+};
+#define PHOS_MAX_LOBES 8 /* bsdf_t::MaxLobes */
+
+typedef struct phos_lobe {
+  uint32_t type;      /* PHOS_LOBE_*            */
+  float    weight[3]; /* closure weight (color) */
+  float    param;
+} phos_lobe;
+
 typedef struct phos_material {
-  uint32_t kind;      /* PHOS_MAT_*                          */
-  float    cs[3];     /* Cs                                  */
-  float    roughness; /* glossy only (node parameter, not alpha) */
-  float    power;     /* emitter only                        */
+  uint32_t  kind;      /* PHOS_MAT_*                                          */
+  float     cs[3];     /* Cs                                                  */
+  float     roughness; /* diffuse / glossy node parameter (not alpha)         */
+  float     power;     /* emitter / background                                */
+  uint32_t  num_lobes; /* PHOS_MAT_LAYERED only, <= PHOS_MAX_LOBES            */
+  phos_lobe lobes[PHOS_MAX_LOBES];
 } phos_material;
 
 /* camera_t (src/entities/camera.hpp:10-40); to_world is Imath row-vector convention:
@@ -58,6 +85,8 @@ typedef struct phos_scene_desc {
   uint32_t             num_materials;
   const phos_material* materials;
   phos_camera          camera;
+  int32_t              environment; /* material id of the environment (PHOS_MAT_BACKGROUND; scene_t::environment(),
+                                       src/scene.cpp:64-74,126-128) or -1: what a ray that misses adds to the path */
 } phos_scene_desc;
 
 #ifdef __cplusplus

@@ -106,6 +106,11 @@ void orc_film_jitter(uint32_t seed, uint32_t spp, float* jx, float* jy) {
 }
 
 /* ---- derived scene tables ------------------------------------------------------------------------------ */
+/* one lobe of bsdf_t after add_lobe + precompute (bsdf.hpp:52-83, bsdf/params.hpp): p0 / p1 = GGX alpha_x / alpha_y,
+ * Oren-Nayar a / b, eta (reflection, refraction), sheen r */
+enum { BSDF_DIFFUSE_F = 1, BSDF_GLOSSY_F = 2, BSDF_SPECULAR_F = 4, BSDF_REFLECT_F = 8, BSDF_TRANSMIT_F = 16 };
+typedef struct { uint32_t type, flags; v3 w; float p0, p1; } lobe1;
+typedef struct bsdf1 { uint32_t n; lobe1 l[PHOS_MAX_LOBES]; } bsdf1;
 typedef struct {
   const phos_scene_desc* d;
   uint32_t nlights;
@@ -113,8 +118,8 @@ typedef struct {
   float* light_area;
   uint32_t* light_tri_mesh; /* meshid | matid << 16 */
   uint32_t* light_tri_face; /* 3 * face index */
-  float* alpha;             /* per material: GGX alpha after microfacet_t::precompute */
-  v3* emission;             /* per material: (power / pi) * Cs */
+  v3* emission;             /* per material: (power / pi) * Cs (emitter), Cs * power (background) */
+  struct bsdf1* bsdf;       /* per material: the closure list eval_closure would build (material.cpp:218-305) */
 } orc_scene;
 
 static inline v3 vert(const phos_scene_desc* d, uint32_t mesh, uint32_t face3, int k) {
@@ -129,17 +134,66 @@ static float roughness_to_alpha(float roughness) {
   return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 
+/* bsdf_t::add_lobe + T::precompute for one closure */
+static void add_lobe(bsdf1* b, uint32_t type, const float w[3], float param) {
+  if (b->n >= PHOS_MAX_LOBES) return;
+  lobe1* l = &b->l[b->n++];
+  l->type = type;
+  l->w = V(w[0], w[1], w[2]);
+  l->p0 = l->p1 = 0.0f;
+  switch (type) {
+    case PHOS_LOBE_DIFFUSE: l->flags = BSDF_REFLECT_F | BSDF_DIFFUSE_F; break;
+    case PHOS_LOBE_OREN_NAYAR: { /* oren_nayar_t::precompute, params.hpp:37-42 */
+      l->flags = BSDF_REFLECT_F | BSDF_DIFFUSE_F;
+      const float sg = (float)(param * (M_PI / 180.0f)); /* trig::radians */
+      const float s2 = sg * sg;
+      l->p0 = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
+      l->p1 = 0.45f * s2 / (s2 + 0.09f);
+      break;
+    }
+    case PHOS_LOBE_REFLECTION: l->flags = BSDF_REFLECT_F | BSDF_SPECULAR_F; l->p0 = param; break;
+    case PHOS_LOBE_REFRACTION: l->flags = BSDF_TRANSMIT_F | BSDF_SPECULAR_F; l->p0 = param; break;
+    case PHOS_LOBE_MICROFACET: /* add_lobe<microfacet_t>: flags = REFLECT (refract = 0), bsdf.hpp:69-83 */
+      l->flags = BSDF_REFLECT_F;
+      l->p0 = l->p1 = fminf(1.0f, fmaxf(0.0001f, roughness_to_alpha(param)));
+      break;
+    case PHOS_LOBE_SHEEN: l->flags = BSDF_REFLECT_F | BSDF_GLOSSY_F; l->p0 = param; break;
+    case PHOS_LOBE_TRANSPARENT: l->flags = BSDF_TRANSMIT_F; break; /* empty_params_t, material.cpp:98-103 */
+    default: b->n--; break;
+  }
+}
+
 void* orc_scene_create(const phos_scene_desc* d) {
   orc_scene* s = (orc_scene*)calloc(1, sizeof(orc_scene));
   s->d = d;
-  s->alpha = (float*)calloc(d->num_materials + 1, sizeof(float));
   s->emission = (v3*)calloc(d->num_materials + 1, sizeof(v3));
+  s->bsdf = (bsdf1*)calloc(d->num_materials + 1, sizeof(bsdf1));
   for (uint32_t m = 0; m < d->num_materials; ++m) {
     const phos_material* mt = &d->materials[m];
-    const float r2 = mt->roughness * mt->roughness; /* glossy_bsdf_node.osl:26 */
-    s->alpha[m] = fminf(1.0f, fmaxf(0.0001f, roughness_to_alpha(r2)));
-    const float k = (float)(mt->power / M_PI); /* diffuse_emitter_node.osl:18 */
-    s->emission[m] = V(1.0f * (k * mt->cs[0]), 1.0f * (k * mt->cs[1]), 1.0f * (k * mt->cs[2]));
+    const float one[3] = {1.0f * mt->cs[0], 1.0f * mt->cs[1], 1.0f * mt->cs[2]}; /* w * component->w, w = (1,1,1) */
+    switch (mt->kind) {
+      case PHOS_MAT_DIFFUSE: /* diffuse_bsdf_node.osl:20-25 */
+        if (mt->roughness == 0) add_lobe(&s->bsdf[m], PHOS_LOBE_DIFFUSE, one, 0.0f);
+        else add_lobe(&s->bsdf[m], PHOS_LOBE_OREN_NAYAR, one, mt->roughness);
+        break;
+      case PHOS_MAT_GLOSSY: /* glossy_bsdf_node.osl:26-34 */
+        if (mt->roughness == 0.0f) add_lobe(&s->bsdf[m], PHOS_LOBE_REFLECTION, one, 0.0f);
+        else add_lobe(&s->bsdf[m], PHOS_LOBE_MICROFACET, one, mt->roughness * mt->roughness);
+        break;
+      case PHOS_MAT_EMITTER: { /* diffuse_emitter_node.osl:18 */
+        const float k = (float)(mt->power / M_PI);
+        s->emission[m] = V(1.0f * (k * mt->cs[0]), 1.0f * (k * mt->cs[1]), 1.0f * (k * mt->cs[2]));
+        break;
+      }
+      case PHOS_MAT_BACKGROUND: /* background_node.osl: Cs * power * background() */
+        s->emission[m] = V(1.0f * (mt->cs[0] * mt->power), 1.0f * (mt->cs[1] * mt->power), 1.0f * (mt->cs[2] * mt->power));
+        break;
+      case PHOS_MAT_LAYERED:
+        for (uint32_t k = 0; k < mt->num_lobes && k < PHOS_MAX_LOBES; ++k)
+          add_lobe(&s->bsdf[m], mt->lobes[k].type, mt->lobes[k].weight, mt->lobes[k].param);
+        break;
+      default: break;
+    }
   }
   /* lights: one per emissive face set, mesh -> set order (mesh.cpp:108-116, scene.cpp:49-55) */
   uint32_t nl = 0, nt = 0;
@@ -179,7 +233,7 @@ void orc_scene_destroy(void* h) {
   orc_scene* s = (orc_scene*)h;
   if (!s) return;
   free(s->light_first); free(s->light_area); free(s->light_tri_mesh); free(s->light_tri_face);
-  free(s->alpha); free(s->emission); free(s);
+  free(s->bsdf); free(s->emission); free(s);
 }
 uint32_t orc_scene_num_lights(void* h) { return ((orc_scene*)h)->nlights; }
 
@@ -314,6 +368,205 @@ static float ct_sample(v3 n, float ax, float ay, v3 wi, v3* wo, float u, float v
   return ct_f(n, ax, ay, wi, *wo);
 }
 
+/* ---- the other lobes and bsdf_t itself ------------------------------------------------------------------------ */
+/* oren_nayar::f, bsdf/oren_nayar.hpp:9-47 */
+static float oren_nayar_f(v3 n, float a, float b, v3 wi, v3 wo) {
+  const base_t base = make_base(n);
+  const v3 li = to_local(&base, wi), lo = to_local(&base, wo);
+  const float cos_theta_i = fabsf(li.y), cos_theta_o = fabsf(lo.y);
+  const float sin_theta_i = sin_theta(li), sin_theta_o = sin_theta(lo);
+  float max_cos = 0.0f;
+  if (sin_theta_i > 0.0001f && sin_theta_o > 0.0001f) {
+    const float sin_phi_i = sin_phi(li), cos_phi_i = cos_phi(li);
+    const float sin_phi_o = sin_phi(lo), cos_phi_o = cos_phi(lo);
+    const float dcos = cos_phi_i * cos_phi_o + sin_phi_i * sin_phi_o;
+    max_cos = fmaxf(0.0f, dcos);
+  }
+  float sin_alpha, tan_beta;
+  if (cos_theta_i > cos_theta_o) {
+    sin_alpha = sin_theta_o;
+    tan_beta = sin_theta_i / cos_theta_i;
+  } else {
+    sin_alpha = sin_theta_i;
+    tan_beta = sin_theta_o / cos_theta_o;
+  }
+  const float result = (a + b * max_cos * sin_alpha * tan_beta);
+  return (float)(result * M_1_PI);
+}
+/* microfacet::sheen, bsdf/sheen.hpp:15-66.  The reference keeps L(0.5, r) in a function-local static that is
+ * initialised by the FIRST sheen lobe ever evaluated (sheen.hpp:56); here it is that of the lobe at hand —
+ * identical as long as a scene uses one sheen roughness. */
+static float sheen_L(float x, float r) {
+  static const float p0[] = {25.3245f, 3.32435f, 0.16801f, -1.27393f, -4.85967f};
+  static const float p1[] = {21.5473f, 3.82987f, 0.19823f, -1.97760f, -4.32054f};
+  const float t = (1.0f - r) * (1.0f - r);
+#define SHEEN_INTERP(i) (t * p0[i] + (1.0f - t) * p1[i])
+  const float a = SHEEN_INTERP(0), b = SHEEN_INTERP(1), c = SHEEN_INTERP(2), d = SHEEN_INTERP(3), e = SHEEN_INTERP(4);
+#undef SHEEN_INTERP
+  const float xc = powf(x, c);
+  return a / (1 + b * xc) + d * x + e;
+}
+static float sheen_D(float r, v3 v) {
+  const float st = sin_theta(v);
+  const float oor = 1.0f / r;
+  return (float)((2.0f + oor) * powf(st, oor) / (2.0f * M_PI));
+}
+static float sheen_Lambda(float r, v3 v) {
+  const float L5 = sheen_L(0.5f, r);
+  const float ct = v.y;
+  const float l = (ct < 0.5f) ? sheen_L(ct, r) : 2.0f * L5 - sheen_L(1.0f - ct, r);
+  return expf(l);
+}
+/* cook_torrance::f with the sheen distribution (bsdf.cpp:88-96, microfacet.hpp:174-215) */
+static float sheen_f(v3 n, float r, v3 wi, v3 wo) {
+  const base_t base = make_base(n);
+  const v3 li = to_local(&base, wi), lo = to_local(&base, wo);
+  if (!((li.y * lo.y) > 0.0f)) return 0.0f;
+  v3 wh = add(li, lo);
+  const float cos_ti = fabsf(li.y), cos_to = fabsf(lo.y);
+  if (cos_ti == 0 || cos_to == 0) return 0.0f;
+  if (wh.x == 0 || wh.y == 0 || wh.z == 0) return 0.0f;
+  wh = normalized(wh);
+  const float d = sheen_D(r, wh);
+  const float g = 1.0f / (1.0f + sheen_Lambda(r, li) + sheen_Lambda(r, lo));
+  const float whu = (float)(wh.x * 0.0f + wh.y * 1.0 + wh.z * 0.0f);
+  const float f = fresnel_dielectric(dot(lo, whu < 0.0f ? neg(wh) : wh), 0.5f);
+  return d * g * f * (1.0f / (4.0f * cos_ti * cos_to));
+}
+/* cook_torrance::pdf, microfacet.hpp:217-236 — G1 is handed the WORLD-space wi there, as here */
+static float ct_pdf(v3 n, float ax, float ay, v3 wi, v3 wo) {
+  const base_t base = make_base(n);
+  const v3 li = to_local(&base, wi), lo = to_local(&base, wo);
+  if (!((li.y * lo.y) > 0.0f)) return 0.0f;
+  const v3 wh = normalized(add(li, lo));
+  return (ggx_D(ax, ay, wh) * ggx_G1(ax, ay, wi) * fabsf(dot(li, wh)) / fabsf(li.y)) / (4.0f * dot(li, wh));
+}
+/* sample::hemisphere::cosine_weighted + orthogonal_base_t::to_world (math/sampling.hpp:23-36) */
+static v3 cosine_sample(v3 n, float sx, float sy, float* pdf) {
+  const base_t base = make_base(n);
+  const float rr = sqrtf(sx);
+  const float theta = (float)(2 * M_PI * sy);
+  const float x = rr * cosf(theta), y = rr * sinf(theta);
+  const v3 lo = V(x, sqrtf(fmaxf(0.0f, 1.0f - sx)), y);
+  *pdf = lo.y * (float)(1.0f / M_PI);
+  return to_world(&base, lo);
+}
+/* eval(), bsdf.cpp:25-107: grey value of one lobe and its pdf */
+static float lobe_eval(const lobe1* l, v3 n, v3 wi, v3 wo, float* pdf) {
+  switch (l->type) {
+    case PHOS_LOBE_DIFFUSE: *pdf = (float)(dot(n, wi) * M_1_PI); return (float)M_1_PI;
+    case PHOS_LOBE_OREN_NAYAR: *pdf = (float)(dot(n, wi) * M_1_PI); return oren_nayar_f(n, l->p0, l->p1, wi, wo);
+    case PHOS_LOBE_MICROFACET: *pdf = ct_pdf(n, l->p0, l->p1, wi, wo); return ct_f(n, l->p0, l->p1, wi, wo);
+    case PHOS_LOBE_SHEEN: *pdf = (float)(dot(n, wi) * M_1_PI); return sheen_f(n, l->p0, wi, wo);
+    default: *pdf = 0.0f; return 0.0f; /* Reflection, Refraction, Transparent */
+  }
+}
+/* bsdf_t::f, bsdf.cpp:113-131 */
+static v3 bsdf_f(const bsdf1* b, v3 n, v3 wi, v3 wo) {
+  v3 out = V(0, 0, 0);
+  for (uint32_t i = 0; i < b->n; ++i) {
+    float ignored;
+    const float e = lobe_eval(&b->l[i], n, wi, wo, &ignored);
+    const float atl = dot(n, wi);
+    const int reflect = atl * dot(n, wo) > 0.0f;
+    if ((reflect && (b->l[i].flags & BSDF_REFLECT_F)) || (!reflect && (b->l[i].flags & BSDF_TRANSMIT_F)))
+      out = add(out, scl(mul(V(e, e, e), b->l[i].w), atl));
+  }
+  return out;
+}
+/* bsdf_t::sample, bsdf.cpp:133-248.  Returns 0 when the path ends (black sample or pdf 0; a lobe that bails out
+ * before setting its pdf leaves the reference with an uninitialised one — frozen to "path ends" here). */
+static int bsdf_sample(const bsdf1* b, v3 n, float sx, float sy, v3 wi, v3* wo, v3* f, float* opdf, uint32_t* oflags) {
+  if (b->n == 0) return 0;
+  uint32_t index = (uint32_t)floorf(sx * b->n);
+  if (index > b->n - 1) index = b->n - 1;
+  const float u = fminf(sx * b->n - index, 1.0f - FLT_EPSILON);
+  const lobe1* l = &b->l[index];
+  float pdf = 0.0f, r = 0.0f;
+  switch (l->type) {
+    case PHOS_LOBE_DIFFUSE: *wo = cosine_sample(n, u, sy, &pdf); r = (float)M_1_PI; break;
+    case PHOS_LOBE_OREN_NAYAR: *wo = cosine_sample(n, u, sy, &pdf); r = oren_nayar_f(n, l->p0, l->p1, wi, *wo); break;
+    case PHOS_LOBE_MICROFACET:
+      r = ct_sample(n, l->p0, l->p1, wi, wo, u, sy, &pdf);
+      if (r == 0.0f) return 0;
+      break;
+    case PHOS_LOBE_SHEEN: *wo = cosine_sample(n, u, sy, &pdf); r = sheen_f(n, l->p0, wi, *wo); break;
+    case PHOS_LOBE_REFLECTION: { /* reflection.hpp:8-21 */
+      const float ct = dot(n, wi);
+      pdf = 1.0f;
+      *wo = add(neg(wi), scl(n, 2.0f * ct));
+      r = 1.0f;
+      break;
+    }
+    case PHOS_LOBE_REFRACTION: { /* refraction.hpp:10-46 */
+      pdf = 1.0f;
+      float ct = dot(n, wi);
+      const float st = fmaxf(0.0f, 1.0f - ct * ct);
+      v3 nn;
+      float eta = l->p0;
+      if (ct > 0) { nn = n; eta = 1.0f / eta; }
+      else { nn = neg(n); ct = -ct; }
+      const float arg = 1.0f - (eta * eta * st);
+      if (!(arg >= 0.0f)) return 0; /* total internal reflection: black */
+      const float dnp = sqrtf(arg);
+      const float nk = eta * ct - dnp;
+      *wo = add(scl(neg(wi), eta), scl(nn, nk));
+      r = 1.0f;
+      break;
+    }
+    case PHOS_LOBE_TRANSPARENT: *wo = neg(wi); pdf = 1.0f; r = 1.0f; break;
+    default: return 0;
+  }
+  if (pdf == 0.0f) return 0;
+  v3 result = mul(V(r, r, r), l->w);
+  int matched = 1;
+  for (uint32_t i = 0; i < b->n; ++i) {
+    if (i == index || (l->flags & b->l[i].flags) != b->l[i].flags) continue;
+    const int reflect = dot(n, wi) * dot(n, *wo) > 0.0f;
+    if ((reflect && (b->l[i].flags & BSDF_REFLECT_F)) || (!reflect && (b->l[i].flags & BSDF_TRANSMIT_F))) {
+      float lobe_pdf = 0.0f;
+      const float e = lobe_eval(&b->l[i], n, wi, *wo, &lobe_pdf);
+      result = add(result, mul(V(e, e, e), b->l[i].w));
+      pdf += lobe_pdf;
+      ++matched;
+    }
+  }
+  pdf /= matched;
+  *f = result;
+  *opdf = pdf;
+  *oflags = l->flags;
+  return 1;
+}
+
+/* parity hooks: bsdf_t::f / bsdf_t::sample of one material for given directions (tests pin them to the compiled
+ * reference's own bsdf_t) */
+void orc_bsdf_f(const phos_material* mt, const float* n, const float* wi, const float* wo, float* out3) {
+  phos_scene_desc d;
+  memset(&d, 0, sizeof(d));
+  d.num_materials = 1;
+  d.materials = mt;
+  orc_scene* S = (orc_scene*)orc_scene_create(&d);
+  const v3 f = bsdf_f(&S->bsdf[0], V(n[0], n[1], n[2]), V(wi[0], wi[1], wi[2]), V(wo[0], wo[1], wo[2]));
+  out3[0] = f.x; out3[1] = f.y; out3[2] = f.z;
+  orc_scene_destroy(S);
+}
+int orc_bsdf_sample(const phos_material* mt, const float* n, const float* wi, float sx, float sy, float* wo3, float* f3,
+                    float* pdf, uint32_t* flags) {
+  phos_scene_desc d;
+  memset(&d, 0, sizeof(d));
+  d.num_materials = 1;
+  d.materials = mt;
+  orc_scene* S = (orc_scene*)orc_scene_create(&d);
+  v3 wo = V(0, 0, 0), f = V(0, 0, 0);
+  *pdf = 0.0f;
+  *flags = 0;
+  const int ok = bsdf_sample(&S->bsdf[0], V(n[0], n[1], n[2]), sx, sy, V(wi[0], wi[1], wi[2]), &wo, &f, pdf, flags);
+  wo3[0] = wo.x; wo3[1] = wo.y; wo3[2] = wo.z;
+  f3[0] = f.x; f3[1] = f.y; f3[2] = f.z;
+  orc_scene_destroy(S);
+  return ok && !(f.x == 0.0f && f.y == 0.0f && f.z == 0.0f) && *pdf != 0.0f; /* what sample_bsdf continues on (spt.hpp:291) */
+}
+
 /* ---- shading normal: mesh_t::shading_parameters, mesh.cpp:169-206 ------------------------------------------ */
 static v3 shading_normal(const phos_scene_desc* d, uint32_t mesh, uint32_t face3, float u, float v) {
   if (d->mesh_smooth[mesh] && d->normals) {
@@ -438,7 +691,10 @@ void orc_render(void* scene_h, const void* nodes, const void* packets, uint32_t 
         uint32_t depth = 0;
         for (;;) {
           trace1(nodes, packets, &r, rcp_mode);
-          if (!(r.flags & ORC_HIT)) break; /* miss: out += beta * e_env, no environment in the subset */
+          if (!(r.flags & ORC_HIT)) { /* miss: out += beta * e_env (spt.hpp:199-202) */
+            if (d->environment >= 0) rad = add(rad, mul(beta, S->emission[d->environment]));
+            break;
+          }
           /* interaction: deferred_shading_kernel.hpp:47-62 */
           const v3 P = add(r.o, scl(r.w, r.d));
           const v3 wo = neg(r.w);
@@ -448,6 +704,7 @@ void orc_render(void* scene_h, const void* nodes, const void* packets, uint32_t 
             normals[3 * (size_t)pixel] = n.x; normals[3 * (size_t)pixel + 1] = n.y; normals[3 * (size_t)pixel + 2] = n.z;
           }
           const phos_material* mt = &d->materials[mat];
+          const bsdf1* bs = &S->bsdf[mat];
           const v3 e = mt->kind == PHOS_MAT_EMITTER ? S->emission[mat] : V(0, 0, 0);
           /* NEE: fresh_light_samples (sampling.cpp:160-180) + light_sampler_t (spt.hpp:116-148) */
           ray1 sh;
@@ -481,26 +738,15 @@ void orc_render(void* scene_h, const void* nodes, const void* packets, uint32_t 
           }
           /* integrate: spt.hpp:161-210 */
           if (depth == 0 || (r.flags & ORC_SPECULAR)) rad = add(rad, mul(beta, e));
-          if (have_light && !(sh.flags & (ORC_HIT | ORC_MASKED)) && mt->kind != PHOS_MAT_EMITTER) {
+          if (have_light && !(sh.flags & (ORC_HIT | ORC_MASKED)) && bs->n != 0) {
             /* li, spt.hpp:212-255 */
-            float fs; /* bsdf_t::f for the single lobe, bsdf.cpp:113-131 */
-            {
-              const float atl = dot(n, sh.w);
-              const int reflect = atl * dot(n, wo) > 0.0f;
-              float ev = mt->kind == PHOS_MAT_DIFFUSE ? (float)M_1_PI : ct_f(n, S->alpha[mat], S->alpha[mat], sh.w, wo);
-              fs = reflect ? 1.0f : 0.0f;
-              if (reflect) {
-                const uint32_t lmesh = sh.mesh & 0xffffu, lmat = sh.mesh >> 16;
-                const v3 light_n = shading_normal(d, lmesh, sh.face, sh.u, sh.v);
-                const v3 le = S->emission[lmat];
-                const float pdf = light_pdf * sh.d * sh.d / fabsf(dot(light_n, neg(sh.w)));
-                const v3 cs = V(mt->cs[0], mt->cs[1], mt->cs[2]);
-                const v3 f = scl(mul(V(ev, ev, ev), cs), atl);           /* e * weight * atl */
-                const v3 li = scl(mul(scl(le, 4), f), 1.0f / pdf);      /* (light.e * 4) * f * (1 / pdf) */
-                rad = add(rad, mul(beta, li));
-              }
-            }
-            (void)fs;
+            const v3 f = bsdf_f(bs, n, sh.w, wo);
+            const uint32_t lmesh = sh.mesh & 0xffffu, lmat = sh.mesh >> 16;
+            const v3 light_n = shading_normal(d, lmesh, sh.face, sh.u, sh.v);
+            const v3 le = S->emission[lmat];
+            const float pdf = light_pdf * sh.d * sh.d / fabsf(dot(light_n, neg(sh.w)));
+            const v3 li = scl(mul(scl(le, 4), f), 1.0f / pdf); /* (light.e * 4) * f * (1 / pdf) */
+            rad = add(rad, mul(beta, li));
           }
           ++depth;
           /* sample_bsdf, spt.hpp:257-305 with terminate_path, :307-328 */
@@ -516,35 +762,22 @@ void orc_render(void* scene_h, const void* nodes, const void* packets, uint32_t 
             beta = scl(beta, wgt);
             if (!alive) break;
           }
-          if (mt->kind == PHOS_MAT_EMITTER) break; /* 0-lobe BSDF: the path ends (difference 3) */
+          if (bs->n == 0) break; /* 0-lobe BSDF (an emitter): the path ends (difference 3) */
           {
-            /* bsdf_t::sample with one lobe: index 0, u = min(sample.x, 1 - eps) (bsdf.cpp:140-148) */
-            const float sx_ = fminf(orc_rnd(seed, pixel, s, depth - 1, DIM_BSDF_U) * 1 - 0, 1.0f - FLT_EPSILON);
+            /* bsdf_t::sample, bsdf.cpp:133-248, then sample_bsdf, spt.hpp:289-303 */
+            const float sx_ = orc_rnd(seed, pixel, s, depth - 1, DIM_BSDF_U);
             const float sy_ = orc_rnd(seed, pixel, s, depth - 1, DIM_BSDF_V);
-            v3 sampled = V(0, 0, 0);
-            float pdf = 0.0f, fv;
-            if (mt->kind == PHOS_MAT_DIFFUSE) { /* lambert::sample, lambert.hpp:24-36 */
-              const base_t base = make_base(n);
-              const float rr = sqrtf(sx_);
-              const float theta = (float)(2 * M_PI * sy_);
-              const float x = rr * cosf(theta), y = rr * sinf(theta);
-              const v3 lo = V(x, sqrtf(fmaxf(0.0f, 1.0f - sx_)), y);
-              pdf = lo.y * (float)(1.0f / M_PI);
-              sampled = to_world(&base, lo);
-              fv = (float)M_1_PI;
-            } else {
-              fv = ct_sample(n, S->alpha[mat], S->alpha[mat], wo, &sampled, sx_, sy_, &pdf);
-              if (fv == 0.0f) break; /* early-outs return black with pdf unset */
-            }
-            if (pdf == 0.0f) break;
-            const v3 f = V(fv * mt->cs[0], fv * mt->cs[1], fv * mt->cs[2]); /* result *= weight[index] */
-            if (f.x == 0.0f && f.y == 0.0f && f.z == 0.0f) break;
+            v3 sampled = V(0, 0, 0), f = V(0, 0, 0);
+            float pdf = 0.0f;
+            uint32_t lflags = 0;
+            if (!bsdf_sample(bs, n, sx_, sy_, wo, &sampled, &f, &pdf, &lflags)) break;
+            if ((f.x == 0.0f && f.y == 0.0f && f.z == 0.0f) || pdf == 0.0f) break;
             const float weight = dot(n, sampled);
             beta = mul(beta, scl(f, fabsf(weight) / pdf));
             r.o = add(P, scl(n, weight < 0.0f ? -0.0001f : 0.0001f)); /* offset(), math/vector.hpp:14-21 */
             r.w = sampled;
             r.d = FLT_MAX;
-            r.flags = 0; /* neither lobe of the subset is SPECULAR */
+            r.flags = (lflags & BSDF_SPECULAR_F) ? ORC_SPECULAR : 0; /* rays->specular_bounce, spt.hpp:302 */
           }
         }
         out[0] += rad.x * scale; /* channel_t::add, cpu.cpp:191 */

@@ -54,6 +54,9 @@ class Oracle:
         L.orc_rnd.restype = C.c_float
         L.orc_rnd.argtypes = [C.c_uint32] * 5
         L.orc_film_jitter.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_bsdf_f.argtypes = [C.c_void_p] * 5
+        L.orc_bsdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float] + [C.c_void_p] * 4
+        L.orc_bsdf_sample.restype = C.c_int
         L.orc_camera_rays_lens.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
 
     def brute_force(self, packets: np.ndarray, rays: RayBatch) -> RayBatch:
@@ -95,6 +98,28 @@ class Oracle:
                             1 if rcp_mode else 0, film.ctypes.data, normals.ctypes.data if normals is not None else None)
         self.lib.orc_scene_destroy(h)
         return film
+
+    def _mat_ptr(self, scene: Scene, mat: int):
+        d = scene.desc()
+        return d, C.addressof(d.materials[mat])
+
+    def bsdf_f(self, scene: Scene, mat: int, n, wi, wo) -> np.ndarray:
+        """bsdf_t::f of material `mat` at shading normal n (restatement)."""
+        d, mp = self._mat_ptr(scene, mat)
+        a = [np.ascontiguousarray(x, np.float32) for x in (n, wi, wo)]
+        out = np.zeros(3, np.float32)
+        self.lib.orc_bsdf_f(mp, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, out.ctypes.data)
+        return out
+
+    def bsdf_sample(self, scene: Scene, mat: int, n, wi, sx: float, sy: float):
+        """bsdf_t::sample (restatement): (alive, wo, f, pdf, flags)."""
+        d, mp = self._mat_ptr(scene, mat)
+        a = [np.ascontiguousarray(x, np.float32) for x in (n, wi)]
+        wo, f = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        pdf, fl = C.c_float(0), C.c_uint32(0)
+        ok = self.lib.orc_bsdf_sample(mp, a[0].ctypes.data, a[1].ctypes.data, sx, sy, wo.ctypes.data, f.ctypes.data,
+                                      C.addressof(pdf), C.addressof(fl))
+        return bool(ok), wo, f, pdf.value, fl.value
 
     def camera_rays_lens(self, scene: Scene, x0, y0, w, h, jx, jy, lens_u, lens_v, rcp_mode: bool = False):
         """camera::perspective_kernel_t for the rectangle with one film jitter and one lens sample per slot
@@ -174,6 +199,21 @@ class RefScene:
         self.lib.ref_camera_rays(self.h, x0, y0, w, h, jx, jy, lu.ctypes.data, lv.ctypes.data, *[a.ctypes.data for a in out])
         return np.stack(out[:3], 1), np.stack(out[3:], 1)
 
+    def bsdf_f(self, mat: int, n, wi, wo) -> np.ndarray:
+        """The reference's own bsdf_t::f for material `mat` (built through material_t::evaluate)."""
+        a = [np.ascontiguousarray(x, np.float32) for x in (n, wi, wo)]
+        out = np.zeros(3, np.float32)
+        self.lib.ref_bsdf_f(self.h, mat, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, out.ctypes.data)
+        return out
+
+    def bsdf_sample(self, mat: int, n, wi, sx: float, sy: float):
+        a = [np.ascontiguousarray(x, np.float32) for x in (n, wi)]
+        wo, f = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        pdf, fl = C.c_float(0), C.c_uint32(0)
+        ok = self.lib.ref_bsdf_sample(self.h, mat, a[0].ctypes.data, a[1].ctypes.data, sx, sy, wo.ctypes.data, f.ctypes.data,
+                                      C.addressof(pdf), C.addressof(fl))
+        return bool(ok), wo, f, pdf.value, fl.value
+
     def num_lights(self):
         return self.lib.ref_scene_num_lights(self.h)
 
@@ -211,6 +251,9 @@ class RefLib:
         L.ref_render_on.restype = C.c_double
         L.ref_render_aov.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_render_aov.restype = C.c_double
+        L.ref_bsdf_f.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
+        L.ref_bsdf_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float] + [C.c_void_p] * 4
+        L.ref_bsdf_sample.restype = C.c_int
         L.ref_camera_rays.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_float, C.c_float] + [C.c_void_p] * 8
         L.ref_cuda_device_count.restype = C.c_int
         L.ref_hardware_concurrency.restype = C.c_uint32

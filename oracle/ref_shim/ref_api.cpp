@@ -9,6 +9,7 @@
 #include "../../include/phos_scene.h"
 
 #include "accel/bvh.hpp"
+#include "bsdf.hpp"
 #include "accel/bvh/binned_sah_builder.hpp"
 #include "accel/triangle.hpp"
 #include "kernels/cpu/linear_bvh_kernel.hpp"
@@ -45,13 +46,24 @@ void fill_scene(scene_t& scene, const phos_scene_desc* d) {
     auto* mat = new material_t();
     material_t::builder_t::scoped_t b(mat->builder());
     const char* node = m.kind == PHOS_MAT_EMITTER ? "diffuse_emitter_node"
-                     : m.kind == PHOS_MAT_GLOSSY ? "glossy_bsdf_node" : "diffuse_bsdf_node";
+                     : m.kind == PHOS_MAT_GLOSSY ? "glossy_bsdf_node"
+                     : m.kind == PHOS_MAT_BACKGROUND ? "background_node"
+                     : m.kind == PHOS_MAT_LAYERED ? "layered_node" : "diffuse_bsdf_node";
     b->shader(node, "layer0", "surface");
     b->parameter("Cs", Imath::Color3f(m.cs[0], m.cs[1], m.cs[2]));
     b->parameter("roughness", m.roughness);
     b->parameter("power", m.power);
+    for (uint32_t k = 0; k < m.num_lobes && k < PHOS_MAX_LOBES; ++k) {
+      const std::string p = "lobe" + std::to_string(k) + ".";
+      b->parameter(p + "type", (int)m.lobes[k].type);
+      b->parameter(p + "weight", Imath::Color3f(m.lobes[k].weight[0], m.lobes[k].weight[1], m.lobes[k].weight[2]));
+      b->parameter(p + "param", m.lobes[k].param);
+    }
     scene.add("material" + std::to_string(i), mat);
   }
+  // scene.add(light_t::make_infinite(material)) as codecs/scene.cpp:34-38 does for world.environment
+  if (d->environment >= 0 && (uint32_t)d->environment < d->num_materials)
+    scene.add(light_t::make_infinite(scene.material("material" + std::to_string(d->environment))));
   for (uint32_t m = 0; m < d->num_meshes; ++m) {
     auto* mesh = new mesh_t();
     {
@@ -313,6 +325,42 @@ int ref_cuda_device_count(void) { return cuda_t::device_count(); }
 
 uint32_t ref_hardware_concurrency(void) { return std::thread::hardware_concurrency(); }
 
+
+// material_t::evaluate(allocator, hits, active) for one slot with shading normal n -> the slot's bsdf_t
+static bsdf_t* build_bsdf(ref_scene* s, uint32_t mat, const float* n, allocator_t& allocator) {
+  interaction_t<>* hits = new (allocator) interaction_t<>();
+  hits->n.from(0, Imath::V3f(n[0], n[1], n[2]));
+  active_t<> active;
+  active.reset(0);
+  active.num = 1;
+  active.index[0] = 0;
+  s->scene.material(mat)->evaluate(allocator, hits, active);
+  return hits->bsdf[0];
+}
+
+// bsdf_t::f / bsdf_t::sample (src/bsdf.cpp:113-248) of material `mat` of the scene at shading normal n: the material
+// builds its bsdf_t exactly as in a render (material_t::evaluate -> add_lobe + precompute), the rest is the
+// reference's own code.
+void ref_bsdf_f(ref_scene* s, uint32_t mat, const float* n, const float* wi, const float* wo, float* out3) {
+  allocator_t allocator(1 << 22);
+  bsdf_t* bsdf = build_bsdf(s, mat, n, allocator);
+  const auto f = bsdf->f(Imath::V3f(wi[0], wi[1], wi[2]), Imath::V3f(wo[0], wo[1], wo[2]));
+  out3[0] = f.x; out3[1] = f.y; out3[2] = f.z;
+}
+int ref_bsdf_sample(ref_scene* s, uint32_t mat, const float* n, const float* wi, float sx, float sy, float* wo3, float* f3,
+                    float* pdf, uint32_t* flags) {
+  allocator_t allocator(1 << 22);
+  bsdf_t* bsdf = build_bsdf(s, mat, n, allocator);
+  Imath::V3f wo(0.0f);
+  float p = 0.0f;  // a lobe that bails out early leaves the caller's pdf untouched: 0 here
+  uint32_t fl = 0;
+  const auto f = bsdf->sample(Imath::V2f(sx, sy), Imath::V3f(wi[0], wi[1], wi[2]), wo, p, fl);
+  wo3[0] = wo.x; wo3[1] = wo.y; wo3[2] = wo.z;
+  f3[0] = f.x; f3[1] = f.y; f3[2] = f.z;
+  *pdf = p;
+  *flags = fl;
+  return !(f.x == 0.0f && f.y == 0.0f && f.z == 0.0f) && p != 0.0f;
+}
 
 // camera::perspective_kernel_t (src/kernels/cpu/camera.hpp:78-159) on one tile with caller-chosen samples:
 // one film jitter for the whole tile, one lens sample per slot (slot = y * tile.w + x; tile.w % 8 == 0,

@@ -14,11 +14,19 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-MAT_DIFFUSE, MAT_GLOSSY, MAT_EMITTER = 0, 1, 2
+MAT_DIFFUSE, MAT_GLOSSY, MAT_EMITTER, MAT_BACKGROUND, MAT_LAYERED = 0, 1, 2, 3, 4
+# closure ids = bsdf_t::type_t (src/bsdf.hpp:14-24)
+LOBE_DIFFUSE, LOBE_OREN_NAYAR, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_MICROFACET, LOBE_SHEEN, LOBE_TRANSPARENT = 1, 2, 4, 8, 16, 32, 128
+MAX_LOBES = 8
+
+
+class PhosLobe(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("weight", C.c_float * 3), ("param", C.c_float)]
 
 
 class PhosMaterial(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("cs", C.c_float * 3), ("roughness", C.c_float), ("power", C.c_float)]
+    _fields_ = [("kind", C.c_uint32), ("cs", C.c_float * 3), ("roughness", C.c_float), ("power", C.c_float),
+                ("num_lobes", C.c_uint32), ("lobes", PhosLobe * MAX_LOBES)]
 
 
 class PhosCamera(C.Structure):
@@ -48,6 +56,7 @@ class PhosSceneDesc(C.Structure):
         ("num_materials", C.c_uint32),
         ("materials", C.POINTER(PhosMaterial)),
         ("camera", PhosCamera),
+        ("environment", C.c_int32),
     ]
 
 
@@ -59,9 +68,32 @@ class Material:
     cs: tuple = (1.0, 1.0, 1.0)
     roughness: float = 0.0
     power: float = 1.0
+    lobes: tuple = ()  # MAT_LAYERED: ((LOBE_*, (r, g, b), param), ...), at most 8
 
     def is_emitter(self) -> bool:  # material_t::is_emitter, src/material.cpp:487-489
         return self.kind == MAT_EMITTER
+
+    @staticmethod
+    def mix(a: "Material", b: "Material", fac: float) -> "Material":
+        """mix_closure_node.osl:20: A * (1 - fac) + B * fac, flattened the way eval_closure walks the MUL / ADD
+        tree (src/material.cpp:218-305): A's closures first with weights * (1 - fac), then B's * fac."""
+        out = []
+        for m, k in ((a, np.float32(1.0) - np.float32(fac)), (b, np.float32(fac))):
+            for (t, w, prm) in m.closures():
+                out.append((t, tuple(float(np.float32(k) * np.float32(c)) for c in w), prm))
+        assert len(out) <= MAX_LOBES
+        return Material(MAT_LAYERED, lobes=tuple(out))
+
+    def closures(self):
+        """The closure list the node hands to eval_closure: (type, weight, param) per lobe."""
+        if self.kind == MAT_LAYERED:
+            return list(self.lobes)
+        if self.kind == MAT_DIFFUSE:  # diffuse_bsdf_node.osl:20-25
+            return [(LOBE_DIFFUSE, self.cs, 0.0)] if self.roughness == 0 else [(LOBE_OREN_NAYAR, self.cs, self.roughness)]
+        if self.kind == MAT_GLOSSY:  # glossy_bsdf_node.osl:26-34
+            r2 = float(np.float32(self.roughness) * np.float32(self.roughness))
+            return [(LOBE_REFLECTION, self.cs, 0.0)] if self.roughness == 0 else [(LOBE_MICROFACET, self.cs, r2)]
+        return []
 
 
 @dataclass
@@ -121,6 +153,7 @@ class Scene:
         self.meshes: list[Mesh] = []
         self.materials: list[Material] = []
         self.camera = Camera()
+        self.environment: int | None = None  # material id of the environment (MAT_BACKGROUND), scene_t::environment()
         self._keep = None
 
     # scene_t::add(name, material) / add(mesh): ids are assigned in insertion order (scene.cpp:85-98)
@@ -175,6 +208,11 @@ class Scene:
             mats[i].cs = (C.c_float * 3)(*m.cs)
             mats[i].roughness = m.roughness
             mats[i].power = m.power
+            mats[i].num_lobes = len(m.lobes)
+            for k, (t, w, prm) in enumerate(m.lobes):
+                mats[i].lobes[k].type = t
+                mats[i].lobes[k].weight = (C.c_float * 3)(*w)
+                mats[i].lobes[k].param = prm
 
         def p(a, t):
             return a.ctypes.data_as(C.POINTER(t)) if a is not None else C.POINTER(t)()
@@ -203,6 +241,7 @@ class Scene:
         d.camera.aperture_radius = cam.aperture_radius
         d.camera.film_width = cam.film_width
         d.camera.film_height = cam.film_height
+        d.environment = -1 if self.environment is None else int(self.environment)
         self._keep = (vert_offset, vertices, normals, face_offset, faces, smooth, set_offset, set_material,
                       set_face_offset, set_faces, mats)
         return d

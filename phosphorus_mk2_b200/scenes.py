@@ -218,3 +218,22 @@ def instanced_field(grid: int = 86, width: int = 3840, height: int = 2160) -> Sc
     _quad(v, f, (-e, 0.45 * grid, -e), (e, 0.45 * grid, -e), (e, 0.45 * grid, e), (-e, 0.45 * grid, e), (0, -1, 0))
     s.add(Mesh(np.array(v), np.array(f), [(light, np.arange(2))]))
     return s
+
+
+def cornell_lobes(width: int = 64, height: int = 64, environment: bool = True) -> Scene:
+    """The Cornell box re-dressed with every closure of the widened subset: Oren-Nayar walls,
+    a mirror short box, a glass (sharp refraction) + sheen mix on the tall box, a diffuse / GGX mix on the floor
+    side walls, a transparent panel in front, and a constant background seen through the open front."""
+    from .scene import (LOBE_REFRACTION, LOBE_SHEEN, LOBE_TRANSPARENT, MAT_BACKGROUND, MAT_DIFFUSE, MAT_GLOSSY, MAT_LAYERED,
+                        Material)
+    sc = cornell_box(width, height)
+    white, red, green, box = 0, 1, 2, 3  # cornell_box's material order: white, red, green, tall box, emitter
+    sc.materials[white] = Material(MAT_DIFFUSE, (0.73, 0.73, 0.73), roughness=20.0)  # oren_nayar(N, 20)
+    sc.materials[red] = Material.mix(Material(MAT_DIFFUSE, (0.65, 0.05, 0.05)), Material(MAT_GLOSSY, (0.9, 0.9, 0.9), roughness=0.25), 0.3)
+    sc.materials[green] = Material.mix(Material(MAT_DIFFUSE, (0.12, 0.45, 0.15)),
+                                       Material(MAT_LAYERED, lobes=((LOBE_SHEEN, (0.8, 0.8, 0.8), 0.4),)), 0.5)
+    sc.materials[box] = Material.mix(Material(MAT_GLOSSY, (0.9, 0.9, 0.9), roughness=0.0),
+                                     Material(MAT_LAYERED, lobes=((LOBE_REFRACTION, (0.9, 0.95, 1.0), 1.5),)), 0.6)
+    if environment:
+        sc.environment = sc.add_material(Material(MAT_BACKGROUND, (0.3, 0.4, 0.6), power=0.5))
+    return sc

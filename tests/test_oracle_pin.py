@@ -105,3 +105,62 @@ def test_camera_rays_against_the_compiled_reference_kernel(oracle, reflib, apert
         assert np.allclose(np.linalg.norm(ew, axis=1), 1.0, atol=1e-6)
         if aperture:
             assert np.abs(rp - rp[0]).max() > 1e-3  # origins really are spread over the lens
+
+
+def _lobe_materials():
+    from phosphorus_mk2_b200.scene import (LOBE_DIFFUSE, LOBE_MICROFACET, LOBE_OREN_NAYAR, LOBE_REFLECTION, LOBE_REFRACTION,
+                                           LOBE_SHEEN, LOBE_TRANSPARENT, MAT_DIFFUSE, MAT_GLOSSY, MAT_LAYERED, Material)
+    grey, red = (0.7, 0.7, 0.7), (0.8, 0.2, 0.1)
+    return [
+        Material(MAT_DIFFUSE, grey),                                   # diffuse(N)
+        Material(MAT_DIFFUSE, red, roughness=25.0),                    # oren_nayar(N, 25 deg)
+        Material(MAT_GLOSSY, grey, roughness=0.35),                    # microfacet ggx
+        Material(MAT_GLOSSY, red, roughness=0.0),                      # reflection(N, 0)
+        Material(MAT_LAYERED, lobes=((LOBE_REFRACTION, grey, 1.5),)),  # refraction(N, 1.5)
+        Material(MAT_LAYERED, lobes=((LOBE_SHEEN, red, 0.4),)),        # sheen(N, 0.4)
+        Material(MAT_LAYERED, lobes=((LOBE_TRANSPARENT, grey, 0.0),)), # transparent()
+        Material.mix(Material(MAT_DIFFUSE, red), Material(MAT_GLOSSY, grey, roughness=0.3), 0.4),
+        Material.mix(Material(MAT_DIFFUSE, grey, roughness=15.0), Material(MAT_LAYERED, lobes=((LOBE_SHEEN, red, 0.4),)), 0.3),
+        Material(MAT_LAYERED, lobes=((LOBE_DIFFUSE, grey, 0.0), (LOBE_REFLECTION, red, 0.0), (LOBE_REFRACTION, grey, 1.3),
+                                     (LOBE_MICROFACET, grey, 0.09), (LOBE_TRANSPARENT, red, 0.0))),
+    ]
+
+
+def test_bsdf_restatement_against_the_compiled_reference_bsdf(oracle, reflib):
+    """bsdf_t::f and bsdf_t::sample (src/bsdf.cpp) for every lobe type of the subset and for mixed closure
+    lists, on random shading normals / directions / samples: the restatement against the reference's own
+    bsdf_t, built by material_t::evaluate + add_lobe + precompute inside the compiled reference."""
+    sc = scenes.cornell_box(16, 16)
+    sc.materials = _lobe_materials() + sc.materials[-1:]  # keep one emitter: the reference wants a light
+    for m in sc.meshes:
+        m.sets = [(min(mat, len(sc.materials) - 1) if mat < len(sc.materials) else len(sc.materials) - 1, f) for mat, f in m.sets]
+    sc.meshes[-1].sets = [(len(sc.materials) - 1, f) for _, f in sc.meshes[-1].sets]
+    rs = reflib.scene(sc)
+    rng = np.random.default_rng(17)
+
+    def unit(v):
+        return (v / np.linalg.norm(v)).astype(np.float32)
+
+    checked_f = checked_s = 0
+    for mat in range(len(sc.materials) - 1):
+        for _ in range(60):
+            n, wi, wo = unit(rng.normal(size=3)), unit(rng.normal(size=3)), unit(rng.normal(size=3))
+            want, got = rs.bsdf_f(mat, n, wi, wo), oracle.bsdf_f(sc, mat, n, wi, wo)
+            assert np.allclose(got, want, rtol=2e-5, atol=1e-7, equal_nan=True), (mat, got, want)
+            checked_f += int(np.any(want != 0) and np.isfinite(want).all())
+            sx, sy = float(rng.random(dtype=np.float32)), float(rng.random(dtype=np.float32))
+            ok_r, wo_r, f_r, pdf_r, fl_r = rs.bsdf_sample(mat, n, wi, sx, sy)
+            ok_o, wo_o, f_o, pdf_o, fl_o = oracle.bsdf_sample(sc, mat, n, wi, sx, sy)
+            lobes = sc.materials[mat].closures()
+            picked = lobes[min(int(np.floor(np.float32(sx) * np.float32(len(lobes)))), len(lobes) - 1)]
+            if picked[0] == 8 and not ok_o:
+                # total internal reflection: refraction::sample returns a default-constructed (uninitialised)
+                # Imath::Color3f and leaves wo unset (refraction.hpp:45) — frozen to "black" in the restatement
+                continue
+            assert ok_r == ok_o, (mat, sx, sy, f_r, pdf_r, f_o, pdf_o)
+            if ok_r:
+                assert fl_r == fl_o
+                assert np.allclose(wo_o, wo_r, rtol=1e-4, atol=2e-6), (mat, wo_o, wo_r)
+                assert np.allclose(f_o, f_r, rtol=1e-3, atol=1e-6, equal_nan=True) and abs(pdf_o - pdf_r) <= 1e-3 * abs(pdf_r) + 1e-7, (mat, f_o, f_r, pdf_o, pdf_r)
+                checked_s += 1
+    assert checked_f > 150 and checked_s > 250
