@@ -19,6 +19,8 @@
 
 #include <phos_cuda.h>
 
+#include "light.hpp"
+
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -27,6 +29,8 @@
 // glossy_bsdf_node / diffuse_emitter_node and their Cs, roughness, power): with OSL that is a
 // ShadingSystem::getattribute query on the shader group; the table-driven stand-in answers directly.
 bool material_builtin_closure(const material_t* m, uint32_t* kind, float cs[3], float* roughness, float* power);
+// ... and, for a material whose shader group flattens to a list of closures (mix / add trees): that list
+int material_builtin_lobes(const material_t* m, uint32_t* type, float* weight3, float* param);
 
 namespace {
 
@@ -99,7 +103,17 @@ void flatten(const scene_t& scene, flat_scene_t& f) {
   for (uint32_t i = 0; i < scene.num_materials(); ++i) {
     phos_material pm = {};
     if (!material_builtin_closure(scene.material(i), &pm.kind, pm.cs, &pm.roughness, &pm.power))
-      throw std::runtime_error("cuda_t: material outside the built-in closure subset (diffuse / ggx / emitter)");
+      throw std::runtime_error("cuda_t: material outside the built-in closure set");
+    if (pm.kind == PHOS_MAT_LAYERED) {
+      uint32_t type[PHOS_MAX_LOBES];
+      float weight[3 * PHOS_MAX_LOBES], param[PHOS_MAX_LOBES];
+      pm.num_lobes = (uint32_t)material_builtin_lobes(scene.material(i), type, weight, param);
+      for (uint32_t k = 0; k < pm.num_lobes; ++k) {
+        pm.lobes[k].type = type[k];
+        for (int c = 0; c < 3; ++c) pm.lobes[k].weight[c] = weight[3 * k + c];
+        pm.lobes[k].param = param[k];
+      }
+    }
     f.materials.push_back(pm);
   }
   phos_scene_desc& d = f.desc;
@@ -124,6 +138,8 @@ void flatten(const scene_t& scene, flat_scene_t& f) {
   d.camera.aperture_radius = c.aperture_radius;
   d.camera.film_width = c.film.width;
   d.camera.film_height = c.film.height;
+  // scene_t::environment() (src/scene.cpp:126-128): what a ray that leaves the scene picks up (spt.hpp:199-202)
+  d.environment = scene.environment() ? (int32_t)scene.environment()->matid() : -1;
 }
 
 }  // namespace

@@ -61,11 +61,22 @@ __host__ __device__ __forceinline__ float rng(uint32_t seed, uint32_t pixel, uin
 enum { DIM_LIGHT = 0, DIM_LIGHT_U = 1, DIM_LIGHT_V = 2, DIM_BSDF_U = 3, DIM_BSDF_V = 4, DIM_RR = 5, DIM_LENS = 6, DIM_FILM = 7 };
 
 // ---- scene tables in HBM -------------------------------------------------------------------------------
+// One lobe of bsdf_t after add_lobe + precompute (bsdf.hpp:52-83, bsdf/params.hpp): type = bsdf_t::type_t
+// (= PHOS_LOBE_*), flags = bsdf::REFLECT / TRANSMIT / SPECULAR ..., p0 / p1 = GGX alpha_x / alpha_y, Oren-Nayar
+// a / b, eta (reflection, refraction), sheen r.
+enum { BSDF_DIFFUSE_F = 1, BSDF_GLOSSY_F = 2, BSDF_SPECULAR_F = 4, BSDF_REFLECT_F = 8, BSDF_TRANSMIT_F = 16 };
+struct DevLobe {
+  uint32_t type, flags;
+  float w[3];
+  float p0, p1;
+};
+// What material_t::evaluate leaves in shading_result_t for a hit on this material: the closure list
+// eval_closure builds (material.cpp:218-305) and the emission.
 struct DevMaterial {
-  uint32_t kind;  // PHOS_MAT_*
-  float cs[3];
-  float alpha;  // GGX alpha after microfacet_t::precompute (params.hpp:86-99) of roughness^2
-  float e[3];   // (power / pi) * Cs
+  uint32_t kind;    // PHOS_MAT_*
+  uint32_t nlobes;  // 0 for emitters / the background
+  float e[3];       // (power / pi) * Cs (emitter), Cs * power (background)
+  DevLobe lobes[8];
 };
 
 struct DevScene {
@@ -76,6 +87,7 @@ struct DevScene {
   const uint32_t* face_offset;
   const uint8_t* mesh_smooth;
   const DevMaterial* mats;
+  int32_t environment;  // material id of the environment or -1 (scene_t::environment())
   uint32_t nlights;
   const uint32_t* light_first;     // [nlights + 1]
   const float* light_area;         // [nlights]
@@ -247,6 +259,188 @@ __device__ __forceinline__ float ct_sample(v3 n, float ax, float ay, v3 wi, v3& 
   opdf = dpdf / (4.0f * dot(li, wh));
   wo = to_world(base, lo);
   return ct_f(n, ax, ay, wi, wo);
+}
+
+
+// ---- the other lobes and bsdf_t itself -----------------------------------------------------------------------------
+// oren_nayar::f, bsdf/oren_nayar.hpp:9-47
+__device__ __forceinline__ float oren_nayar_f(v3 n, float a, float b, v3 wi, v3 wo) {
+  const Base base = make_base(n);
+  const v3 li = to_local(base, wi), lo = to_local(base, wo);
+  const float cos_theta_i = fabsf(li.y), cos_theta_o = fabsf(lo.y);
+  const float sin_theta_i = sin_theta(li), sin_theta_o = sin_theta(lo);
+  float max_cos = 0.0f;
+  if (sin_theta_i > 0.0001f && sin_theta_o > 0.0001f) {
+    const float sin_phi_i = sin_phi(li), cos_phi_i = cos_phi(li);
+    const float sin_phi_o = sin_phi(lo), cos_phi_o = cos_phi(lo);
+    const float dcos = cos_phi_i * cos_phi_o + sin_phi_i * sin_phi_o;
+    max_cos = fmaxf(0.0f, dcos);
+  }
+  float sin_alpha, tan_beta;
+  if (cos_theta_i > cos_theta_o) {
+    sin_alpha = sin_theta_o;
+    tan_beta = sin_theta_i / cos_theta_i;
+  } else {
+    sin_alpha = sin_theta_i;
+    tan_beta = sin_theta_o / cos_theta_o;
+  }
+  const float result = (a + b * max_cos * sin_alpha * tan_beta);
+  return (float)(result * PHOS_1_PI);
+}
+// microfacet::sheen, bsdf/sheen.hpp:15-66.  The reference keeps L(0.5, r) in a function-local static initialised by
+// the first sheen lobe ever evaluated (sheen.hpp:56); here it is that of the lobe at hand — identical as long as
+// a scene uses one sheen roughness.
+__device__ __forceinline__ float sheen_L(float x, float r) {
+  const float t = (1.0f - r) * (1.0f - r);
+  const float a = t * 25.3245f + (1.0f - t) * 21.5473f;
+  const float b = t * 3.32435f + (1.0f - t) * 3.82987f;
+  const float c = t * 0.16801f + (1.0f - t) * 0.19823f;
+  const float d = t * -1.27393f + (1.0f - t) * -1.97760f;
+  const float e = t * -4.85967f + (1.0f - t) * -4.32054f;
+  const float xc = powf(x, c);
+  return a / (1 + b * xc) + d * x + e;
+}
+__device__ __forceinline__ float sheen_D(float r, v3 v) {
+  const float st = sin_theta(v);
+  const float oor = 1.0f / r;
+  return (float)((2.0f + oor) * powf(st, oor) / (2.0f * PHOS_PI));
+}
+__device__ __forceinline__ float sheen_Lambda(float r, v3 v) {
+  const float L5 = sheen_L(0.5f, r);
+  const float ct = v.y;
+  const float l = (ct < 0.5f) ? sheen_L(ct, r) : 2.0f * L5 - sheen_L(1.0f - ct, r);
+  return expf(l);
+}
+// cook_torrance::f with the sheen distribution (bsdf.cpp:88-96, microfacet.hpp:174-215)
+__device__ __forceinline__ float sheen_f(v3 n, float r, v3 wi, v3 wo) {
+  const Base base = make_base(n);
+  const v3 li = to_local(base, wi), lo = to_local(base, wo);
+  if (!((li.y * lo.y) > 0.0f)) return 0.0f;
+  v3 wh = add(li, lo);
+  const float cos_ti = fabsf(li.y), cos_to = fabsf(lo.y);
+  if (cos_ti == 0 || cos_to == 0) return 0.0f;
+  if (wh.x == 0 || wh.y == 0 || wh.z == 0) return 0.0f;
+  wh = normalized(wh);
+  const float d = sheen_D(r, wh);
+  const float g = 1.0f / (1.0f + sheen_Lambda(r, li) + sheen_Lambda(r, lo));
+  const float whu = (float)(wh.x * 0.0f + wh.y * 1.0 + wh.z * 0.0f);
+  const float f = fresnel_dielectric(dot(lo, whu < 0.0f ? neg(wh) : wh), 0.5f);
+  return d * g * f * (1.0f / (4.0f * cos_ti * cos_to));
+}
+// cook_torrance::pdf, microfacet.hpp:217-236 — G1 is handed the WORLD-space wi there, as here
+__device__ __forceinline__ float ct_pdf(v3 n, float ax, float ay, v3 wi, v3 wo) {
+  const Base base = make_base(n);
+  const v3 li = to_local(base, wi), lo = to_local(base, wo);
+  if (!((li.y * lo.y) > 0.0f)) return 0.0f;
+  const v3 wh = normalized(add(li, lo));
+  return (ggx_D(ax, ay, wh) * ggx_G1(ax, ay, wi) * fabsf(dot(li, wh)) / fabsf(li.y)) / (4.0f * dot(li, wh));
+}
+// sample::hemisphere::cosine_weighted + orthogonal_base_t::to_world (math/sampling.hpp:23-36, lambert.hpp:24-36)
+__device__ __forceinline__ v3 cosine_sample(v3 n, float sx, float sy, float& pdf) {
+  const Base base = make_base(n);
+  const float rr = sqrtf(sx);
+  const float theta = (float)(2 * PHOS_PI * sy);
+  const float x = rr * cosf(theta), y = rr * sinf(theta);
+  const v3 lo = V(x, sqrtf(fmaxf(0.0f, 1.0f - sx)), y);
+  pdf = lo.y * (float)(1.0f / PHOS_PI);
+  return to_world(base, lo);
+}
+// eval(), bsdf.cpp:25-107: grey value of one lobe and its pdf
+__device__ __forceinline__ float lobe_eval(const DevLobe& l, v3 n, v3 wi, v3 wo, float& pdf) {
+  switch (l.type) {
+    case 1: pdf = (float)(dot(n, wi) * PHOS_1_PI); return (float)PHOS_1_PI;                         // Diffuse
+    case 2: pdf = (float)(dot(n, wi) * PHOS_1_PI); return oren_nayar_f(n, l.p0, l.p1, wi, wo);     // OrenNayar
+    case 16: pdf = ct_pdf(n, l.p0, l.p1, wi, wo); return ct_f(n, l.p0, l.p1, wi, wo);              // Microfacet (GGX)
+    case 32: pdf = (float)(dot(n, wi) * PHOS_1_PI); return sheen_f(n, l.p0, wi, wo);               // Sheen
+    default: pdf = 0.0f; return 0.0f;                                                               // Reflection, Refraction, Transparent
+  }
+}
+// bsdf_t::f, bsdf.cpp:113-131
+__device__ __forceinline__ v3 bsdf_f(const DevMaterial* __restrict__ m, v3 n, v3 wi, v3 wo) {
+  v3 out = V(0, 0, 0);
+  const uint32_t nl = m->nlobes;
+  for (uint32_t i = 0; i < nl; ++i) {
+    const DevLobe l = m->lobes[i];
+    float ignored;
+    const float e = lobe_eval(l, n, wi, wo, ignored);
+    const float atl = dot(n, wi);
+    const bool reflect = atl * dot(n, wo) > 0.0f;
+    if ((reflect && (l.flags & BSDF_REFLECT_F)) || (!reflect && (l.flags & BSDF_TRANSMIT_F)))
+      out = add(out, scl(mul(V(e, e, e), V(l.w[0], l.w[1], l.w[2])), atl));
+  }
+  return out;
+}
+// bsdf_t::sample, bsdf.cpp:133-248.  false when the path ends (a lobe that bails out before setting its pdf
+// leaves the reference with an uninitialised one — frozen to "path ends"; the same for total internal reflection,
+// where refraction::sample returns an uninitialised colour, refraction.hpp:45).
+__device__ __forceinline__ bool bsdf_sample(const DevMaterial* __restrict__ m, v3 n, float sx, float sy, v3 wi, v3& wo, v3& f,
+                                            float& opdf, uint32_t& oflags) {
+  const uint32_t nl = m->nlobes;
+  if (nl == 0) return false;
+  const uint32_t index = min((uint32_t)floorf(sx * nl), nl - 1);
+  const float u = fminf(sx * nl - index, 1.0f - FLT_EPSILON);
+  const DevLobe l = m->lobes[index];
+  float pdf = 0.0f, r = 0.0f;
+  switch (l.type) {
+    case 1: wo = cosine_sample(n, u, sy, pdf); r = (float)PHOS_1_PI; break;
+    case 2: wo = cosine_sample(n, u, sy, pdf); r = oren_nayar_f(n, l.p0, l.p1, wi, wo); break;
+    case 16:
+      r = ct_sample(n, l.p0, l.p1, wi, wo, u, sy, pdf);
+      if (r == 0.0f) return false;
+      break;
+    case 32: wo = cosine_sample(n, u, sy, pdf); r = sheen_f(n, l.p0, wi, wo); break;
+    case 4: {  // reflection.hpp:8-21
+      const float ct = dot(n, wi);
+      pdf = 1.0f;
+      wo = add(neg(wi), scl(n, 2.0f * ct));
+      r = 1.0f;
+      break;
+    }
+    case 8: {  // refraction.hpp:10-46
+      pdf = 1.0f;
+      float ct = dot(n, wi);
+      const float st = fmaxf(0.0f, 1.0f - ct * ct);
+      v3 nn;
+      float eta = l.p0;
+      if (ct > 0) {
+        nn = n;
+        eta = 1.0f / eta;
+      } else {
+        nn = neg(n);
+        ct = -ct;
+      }
+      const float arg = 1.0f - (eta * eta * st);
+      if (!(arg >= 0.0f)) return false;
+      const float dnp = sqrtf(arg);
+      const float nk = eta * ct - dnp;
+      wo = add(scl(neg(wi), eta), scl(nn, nk));
+      r = 1.0f;
+      break;
+    }
+    case 128: wo = neg(wi); pdf = 1.0f; r = 1.0f; break;  // Transparent
+    default: return false;
+  }
+  if (pdf == 0.0f) return false;
+  v3 result = mul(V(r, r, r), V(l.w[0], l.w[1], l.w[2]));
+  int matched = 1;
+  for (uint32_t i = 0; i < nl; ++i) {
+    if (i == index) continue;
+    const DevLobe o = m->lobes[i];
+    if ((l.flags & o.flags) != o.flags) continue;
+    const bool reflect = dot(n, wi) * dot(n, wo) > 0.0f;
+    if ((reflect && (o.flags & BSDF_REFLECT_F)) || (!reflect && (o.flags & BSDF_TRANSMIT_F))) {
+      float lobe_pdf = 0.0f;
+      const float e = lobe_eval(o, n, wi, wo, lobe_pdf);
+      result = add(result, mul(V(e, e, e), V(o.w[0], o.w[1], o.w[2])));
+      pdf += lobe_pdf;
+      ++matched;
+    }
+  }
+  pdf /= matched;
+  f = result;
+  opdf = pdf;
+  oflags = l.flags;
+  return true;
 }
 
 }  // namespace phos

@@ -176,19 +176,68 @@ int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
   for (uint32_t s = 0; s < nsets; ++s)
     if (d->set_material[s] >= d->num_materials) return fail(ctx, PHOS_ERR_INVALID, "face set with an unknown material");
 
+  if (d->environment >= 0 && ((uint32_t)d->environment >= d->num_materials || d->materials[d->environment].kind != PHOS_MAT_BACKGROUND))
+    return fail(ctx, PHOS_ERR_INVALID, "environment is not a background material of the scene");
+  scene.environment = d->environment;
   std::vector<DevMaterial> mats(std::max<uint32_t>(1, d->num_materials));
+  memset(mats.data(), 0, mats.size() * sizeof(DevMaterial));
+  // bsdf_t::add_lobe + T::precompute for one closure (bsdf.hpp:52-83, bsdf/params.hpp)
+  auto add_lobe = [&](DevMaterial& o, uint32_t type, const float* w, float param) -> bool {
+    if (o.nlobes >= PHOS_MAX_LOBES) return false;
+    DevLobe& l = o.lobes[o.nlobes++];
+    l.type = type;
+    for (int c = 0; c < 3; ++c) l.w[c] = w[c];
+    l.p0 = l.p1 = 0.0f;
+    switch (type) {
+      case PHOS_LOBE_DIFFUSE: l.flags = BSDF_REFLECT_F | BSDF_DIFFUSE_F; return true;
+      case PHOS_LOBE_OREN_NAYAR: {  // oren_nayar_t::precompute, params.hpp:37-42
+        l.flags = BSDF_REFLECT_F | BSDF_DIFFUSE_F;
+        const float sg = (float)(param * (M_PI / 180.0f));
+        const float s2 = sg * sg;
+        l.p0 = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
+        l.p1 = 0.45f * s2 / (s2 + 0.09f);
+        return true;
+      }
+      case PHOS_LOBE_REFLECTION: l.flags = BSDF_REFLECT_F | BSDF_SPECULAR_F; l.p0 = param; return true;
+      case PHOS_LOBE_REFRACTION: l.flags = BSDF_TRANSMIT_F | BSDF_SPECULAR_F; l.p0 = param; return true;
+      case PHOS_LOBE_MICROFACET:  // add_lobe<microfacet_t> with refract = 0: flags = REFLECT (bsdf.hpp:69-83)
+        l.flags = BSDF_REFLECT_F;
+        l.p0 = l.p1 = std::min(1.0f, std::max(0.0001f, roughness_to_alpha(param)));
+        return true;
+      case PHOS_LOBE_SHEEN: l.flags = BSDF_REFLECT_F | BSDF_GLOSSY_F; l.p0 = param; return true;
+      case PHOS_LOBE_TRANSPARENT: l.flags = BSDF_TRANSMIT_F; return true;  // empty_params_t, material.cpp:98-103
+      default: return false;
+    }
+  };
   for (uint32_t m = 0; m < d->num_materials; ++m) {
     const phos_material& in = d->materials[m];
     DevMaterial& o = mats[m];
     o.kind = in.kind;
-    if (in.kind > PHOS_MAT_EMITTER) return fail(ctx, PHOS_ERR_INVALID, "material kind outside the built-in closure subset");
-    if (in.kind == PHOS_MAT_GLOSSY && !(in.roughness > 0.0f))
-      return fail(ctx, PHOS_ERR_INVALID, "glossy roughness 0 is the mirror closure, which is outside the built-in subset");
-    for (int k = 0; k < 3; ++k) o.cs[k] = in.cs[k];
-    const float r2 = in.roughness * in.roughness;  // glossy_bsdf_node.osl:26
-    o.alpha = std::min(1.0f, std::max(0.0001f, roughness_to_alpha(r2)));
-    const float k = (float)(in.power / M_PI);  // diffuse_emitter_node.osl:18
-    for (int c = 0; c < 3; ++c) o.e[c] = 1.0f * (k * in.cs[c]);
+    const float cw[3] = {1.0f * in.cs[0], 1.0f * in.cs[1], 1.0f * in.cs[2]};  // w * component->w with w = (1, 1, 1)
+    bool ok = true;
+    switch (in.kind) {
+      case PHOS_MAT_DIFFUSE:  // diffuse_bsdf_node.osl:20-25
+        ok = in.roughness == 0 ? add_lobe(o, PHOS_LOBE_DIFFUSE, cw, 0.0f) : add_lobe(o, PHOS_LOBE_OREN_NAYAR, cw, in.roughness);
+        break;
+      case PHOS_MAT_GLOSSY:  // glossy_bsdf_node.osl:26-34
+        ok = in.roughness == 0.0f ? add_lobe(o, PHOS_LOBE_REFLECTION, cw, 0.0f)
+                                  : add_lobe(o, PHOS_LOBE_MICROFACET, cw, in.roughness * in.roughness);
+        break;
+      case PHOS_MAT_EMITTER: {  // diffuse_emitter_node.osl:18
+        const float k = (float)(in.power / M_PI);
+        for (int c = 0; c < 3; ++c) o.e[c] = 1.0f * (k * in.cs[c]);
+        break;
+      }
+      case PHOS_MAT_BACKGROUND:  // background_node.osl: Cs * power * background()
+        for (int c = 0; c < 3; ++c) o.e[c] = 1.0f * (in.cs[c] * in.power);
+        break;
+      case PHOS_MAT_LAYERED:
+        if (in.num_lobes > PHOS_MAX_LOBES) return fail(ctx, PHOS_ERR_INVALID, "more than 8 closures in one material (bsdf_t::MaxLobes)");
+        for (uint32_t k = 0; ok && k < in.num_lobes; ++k) ok = add_lobe(o, in.lobes[k].type, in.lobes[k].weight, in.lobes[k].param);
+        break;
+      default: ok = false;
+    }
+    if (!ok) return fail(ctx, PHOS_ERR_INVALID, "material outside the built-in closure set");
   }
   std::vector<uint32_t> light_first, light_tri_mesh, light_tri_face;
   std::vector<float> light_area;

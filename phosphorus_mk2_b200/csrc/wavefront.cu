@@ -152,9 +152,18 @@ __global__ void integrate_kernel(const FrameArgs A, const phos_rays rays, const 
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < A.count[cur];
   bool alive = false;
-  uint32_t q = 0;
+  uint32_t q = 0, nflags = 0;
   v3 no = V(0, 0, 0), nw = V(0, 0, 0);
-  if (valid && (rays.flags[i] & PHOS_HIT)) {  // a miss adds beta * e_env = 0 (no environment in the subset)
+  if (valid && !(rays.flags[i] & PHOS_HIT)) {  // a miss adds beta * e_env (spt.hpp:199-202) and ends the path
+    if (A.scene.environment >= 0) {
+      const uint32_t p = slot_path[i];
+      const size_t Q = A.Q;
+      const DevMaterial* env = A.scene.mats + A.scene.environment;
+      A.rad[p] += A.beta[p] * __ldg(&env->e[0]);
+      A.rad[p + Q] += A.beta[p + Q] * __ldg(&env->e[1]);
+      A.rad[p + 2 * Q] += A.beta[p + 2 * Q] * __ldg(&env->e[2]);
+    }
+  } else if (valid) {
     q = slot_path[i];
     const size_t Q = A.Q;
     const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P];
@@ -165,26 +174,22 @@ __global__ void integrate_kernel(const FrameArgs A, const phos_rays rays, const 
     const v3 P = add(o, scl(w, rays.d[i]));
     const v3 wo = neg(w);
     const v3 n = V(A.n[i], A.n[i + Q], A.n[i + 2 * Q]);
-    const uint32_t mat = rays.mesh[i] >> 16;
-    const DevMaterial mt = A.scene.mats[mat];
-    const bool emitter = mt.kind == PHOS_MAT_EMITTER;
-    const v3 cs = V(mt.cs[0], mt.cs[1], mt.cs[2]);
-    if (emitter && (depth == 0 || (rays.flags[i] & PHOS_SPECULAR))) rad = add(rad, mul(beta, V(mt.e[0], mt.e[1], mt.e[2])));
+    const DevMaterial* mt = A.scene.mats + (rays.mesh[i] >> 16);
+    const bool emitter = __ldg(&mt->kind) == PHOS_MAT_EMITTER;
+    const uint32_t nlobes = __ldg(&mt->nlobes);
+    if (emitter && (depth == 0 || (rays.flags[i] & PHOS_SPECULAR)))
+      rad = add(rad, mul(beta, V(__ldg(&mt->e[0]), __ldg(&mt->e[1]), __ldg(&mt->e[2]))));
     const uint32_t sflags = sh.flags[i];
-    if (!(sflags & (PHOS_HIT | PHOS_MASKED)) && !emitter) {  // li(): a 0-lobe BSDF evaluates to 0
+    if (!(sflags & (PHOS_HIT | PHOS_MASKED)) && nlobes != 0) {  // li(), spt.hpp:212-255; a 0-lobe BSDF evaluates to 0
       const v3 swi = V(sh.wx[i], sh.wy[i], sh.wz[i]);
-      const float atl = dot(n, swi);
-      if (atl * dot(n, wo) > 0.0f) {  // reflective lobes need wi and wo on the same side (bsdf.cpp:122-127)
-        const float ev = mt.kind == PHOS_MAT_DIFFUSE ? (float)PHOS_1_PI : ct_f(n, mt.alpha, mt.alpha, swi, wo);
-        const uint32_t lm = sh.mesh[i];
-        const v3 light_n = shading_normal(A.scene, lm & 0xffffu, sh.face[i], sh.u[i], sh.v[i]);
-        const DevMaterial lmt = A.scene.mats[lm >> 16];
-        const float sd = sh.d[i];
-        const float pdf = A.light_pdf[i] * sd * sd / fabsf(dot(light_n, neg(swi)));
-        const v3 f = scl(mul(V(ev, ev, ev), cs), atl);                                      // e * weight * atl
-        const v3 li = scl(mul(scl(V(lmt.e[0], lmt.e[1], lmt.e[2]), 4), f), 1.0f / pdf);    // (light.e * 4) * f * (1 / pdf)
-        rad = add(rad, mul(beta, li));
-      }
+      const v3 f = bsdf_f(mt, n, swi, wo);
+      const uint32_t lm = sh.mesh[i];
+      const v3 light_n = shading_normal(A.scene, lm & 0xffffu, sh.face[i], sh.u[i], sh.v[i]);
+      const DevMaterial* lmt = A.scene.mats + (lm >> 16);
+      const float sd = sh.d[i];
+      const float pdf = A.light_pdf[i] * sd * sd / fabsf(dot(light_n, neg(swi)));
+      const v3 li = scl(mul(scl(V(__ldg(&lmt->e[0]), __ldg(&lmt->e[1]), __ldg(&lmt->e[2])), 4), f), 1.0f / pdf);  // (light.e * 4) * f * (1 / pdf)
+      rad = add(rad, mul(beta, li));
     }
     ++depth;
     // terminate_path
@@ -197,29 +202,15 @@ __global__ void integrate_kernel(const FrameArgs A, const phos_rays rays, const 
       if (alive) wgt = (1.0f / (1.0f - qq));
     }
     beta = scl(beta, wgt);
-    if (alive && emitter) alive = false;  // 0-lobe BSDF: the path ends on an emitter
+    if (alive && nlobes == 0) alive = false;  // 0-lobe BSDF: the path ends on an emitter
     if (alive) {
-      // bsdf_t::sample with a single lobe: index 0, u = min(sample.x, 1 - eps) (bsdf.cpp:140-148)
-      const float su = fminf(rng(A.seed, pix, s, depth - 1, DIM_BSDF_U) * 1 - 0, 1.0f - FLT_EPSILON);
+      // bsdf_t::sample (bsdf.cpp:133-248), then sample_bsdf (spt.hpp:289-303)
+      const float su = rng(A.seed, pix, s, depth - 1, DIM_BSDF_U);
       const float sv = rng(A.seed, pix, s, depth - 1, DIM_BSDF_V);
-      v3 sampled = V(0, 0, 0);
-      float pdf = 0.0f, fv;
-      if (mt.kind == PHOS_MAT_DIFFUSE) {  // lambert::sample + sample::hemisphere::cosine_weighted
-        const Base base = make_base(n);
-        const float rr = sqrtf(su);
-        const float theta = (float)(2 * PHOS_PI * sv);
-        const float x = rr * cosf(theta), y = rr * sinf(theta);
-        const v3 lo = V(x, sqrtf(fmaxf(0.0f, 1.0f - su)), y);
-        pdf = lo.y * (float)(1.0f / PHOS_PI);
-        sampled = to_world(base, lo);
-        fv = (float)PHOS_1_PI;
-      } else {
-        fv = ct_sample(n, mt.alpha, mt.alpha, wo, sampled, su, sv, pdf);
-        if (fv == 0.0f) alive = false;
-      }
-      if (pdf == 0.0f) alive = false;
-      const v3 f = V(fv * cs.x, fv * cs.y, fv * cs.z);
-      if (f.x == 0.0f && f.y == 0.0f && f.z == 0.0f) alive = false;
+      v3 sampled = V(0, 0, 0), f = V(0, 0, 0);
+      float pdf = 0.0f;
+      alive = bsdf_sample(mt, n, su, sv, wo, sampled, f, pdf, nflags);
+      if (alive && ((f.x == 0.0f && f.y == 0.0f && f.z == 0.0f) || pdf == 0.0f)) alive = false;
       if (alive) {
         const float weight = dot(n, sampled);
         beta = mul(beta, scl(f, fabsf(weight) / pdf));
@@ -251,7 +242,7 @@ __global__ void integrate_kernel(const FrameArgs A, const phos_rays rays, const 
     next.wy[slot] = nw.y;
     next.wz[slot] = nw.z;
     next.d[slot] = 3.402823466e+38f;
-    next.flags[slot] = 0u;  // neither lobe of the subset is SPECULAR
+    next.flags[slot] = (nflags & BSDF_SPECULAR_F) ? PHOS_SPECULAR : 0u;  // rays->specular_bounce (spt.hpp:302)
     next_path[slot] = q;
   }
 }

@@ -47,6 +47,41 @@ def test_cornell_image_matches_oracle(oracle, kind, depth, spp):
     assert np.all(got[..., 3] == 1.0)
 
 
+@pytest.mark.parametrize("depth,spp", [(2, 8), (6, 16)])
+def test_wider_closure_set_matches_oracle(oracle, depth, spp):
+    """Oren-Nayar, mirror reflection (SPECULAR bounces count emission), sharp refraction, sheen, closure mixes
+    and the constant environment (scenes.cornell_lobes): the device image against the restatement (pinned to
+    the compiled reference's bsdf_t value by value) at matched samples."""
+    sc = scenes.cornell_lobes(64, 64)
+    acc = Accel(sc)
+    want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), spp, 1, depth, seed=13)
+    got, _ = render_gpu(sc, acc, spp, depth, 13)
+    assert np.isfinite(got).all() and np.isfinite(want).all()
+    assert mean_rel_err(got, want) < 1e-3
+    dark = scenes.cornell_lobes(64, 64, environment=False)
+    got_dark, _ = render_gpu(dark, acc, spp, depth, 13)
+    assert got[..., :3].mean() > got_dark[..., :3].mean() * 1.02  # the environment is seen through the open front
+
+
+@pytest.mark.parametrize("lobe", ["oren_nayar", "mirror", "glass", "sheen", "transparent"])
+def test_single_closures_match_oracle(oracle, lobe):
+    from phosphorus_mk2_b200.scene import LOBE_REFRACTION, LOBE_SHEEN, LOBE_TRANSPARENT, MAT_LAYERED, Material
+    sc = scenes.cornell_box(48, 48)
+    new = {"oren_nayar": Material(MAT_DIFFUSE, (0.7, 0.6, 0.5), roughness=30.0),
+           "mirror": Material(MAT_GLOSSY, (0.9, 0.9, 0.9), roughness=0.0),
+           "glass": Material(MAT_LAYERED, lobes=((LOBE_REFRACTION, (0.95, 0.95, 0.95), 1.45),)),
+           "sheen": Material(MAT_LAYERED, lobes=((LOBE_SHEEN, (0.8, 0.7, 0.9), 0.5),)),
+           "transparent": Material(MAT_LAYERED, lobes=((LOBE_TRANSPARENT, (0.8, 0.9, 0.8), 0.0),))}[lobe]
+    sc.materials[3] = new  # the tall box
+    if lobe in ("oren_nayar", "sheen"):
+        sc.materials[0] = new  # and the white walls
+    acc = Accel(sc)
+    want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), 8, 1, 5, seed=4)
+    got, _ = render_gpu(sc, acc, 8, 5, 4)
+    assert np.isfinite(got).all()
+    assert mean_rel_err(got, want) < 1e-3
+
+
 def test_thin_lens_camera(oracle):
     """camera_t with aperture_radius != 0 (kernels/cpu/camera.hpp:140-147): primary rays against the oracle's
     restatement (itself pinned bit for bit to the compiled reference kernel) on the renderer's own lens draws,
