@@ -147,7 +147,10 @@ __global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const 
 
 // integrator_t::operator() (spt.hpp:161-210) with li (:212-255), sample_bsdf (:257-305) and
 // terminate_path (:307-328); survivors are appended to the next ray stream.
-__global__ void integrate_kernel(const FrameArgs A, const phos_rays rays, const phos_rays sh,
+#ifndef PHOS_INTEGRATE_MIN_BLOCKS
+#define PHOS_INTEGRATE_MIN_BLOCKS 4  // 64 registers: measured best (profiles/r01_render_variants.log: 1 -> 4 blocks = +13 % on Cornell)
+#endif
+__global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kernel(const FrameArgs A, const phos_rays rays, const phos_rays sh,
                                  const uint32_t* __restrict__ slot_path, int cur, phos_rays next, uint32_t* __restrict__ next_path) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < A.count[cur];
