@@ -353,6 +353,9 @@ def main():
     # ---- end to end through the C ABI with pinned host arrays: e2e ------------------------------------
     dev.camera_rays(tiles, drays)
     pristine = drays.download()
+    # one rank per GPU: stay on the CPUs next to this GPU before allocating the page-locked arrays (first touch),
+    # so the up-copies and the zero-copy result stores do not cross the socket interconnect
+    numa_cpus = dev._L.phos_cuda_bind_host_to_device(local)
     hrays = pinned_ray_batch(n)
     fields = ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags")
 
@@ -446,7 +449,7 @@ def main():
                            "hit_fraction": hits / n, "preprocess_s": prep_s, "wall_s_timed_loop": wall},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 8 * n + 16 * hits,
-                        "steps": e2e_steps, "matches_device_path": e2e_ok},
+                        "steps": e2e_steps, "matches_device_path": e2e_ok, "host_cpus_bound": numa_cpus},
                 "roofline": roof, "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line), flush=True)
     dev.close()

@@ -136,6 +136,10 @@ uint64_t phos_cuda_launch_count(phos_ctx* ctx);
 /* Trace device-resident rays with traversal counters on: total 8-wide nodes box-tested and
  * triangles Moeller-Trumbore-tested over the batch (the N_node / N_tri of the roofline model).  Blocking. */
 int phos_cuda_trace_count(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint64_t* out_nodes, uint64_t* out_tris);
+/* Bind the calling host thread (and threads it spawns later) to the CPUs local to `device` (sysfs local_cpulist of
+ * its PCI function), so page-locked ray arrays allocated afterwards live on the GPU's NUMA node.  One rank per GPU
+ * calls this first.  Returns the number of CPUs bound to, 0 if the topology is not exposed (nothing changes). */
+int phos_cuda_bind_host_to_device(int device);
 /* page-locked host memory for ray streams handed to phos_cuda_trace (pageable memory works, slower) */
 void* phos_cuda_host_alloc(uint64_t bytes);
 void  phos_cuda_host_free(void* p);

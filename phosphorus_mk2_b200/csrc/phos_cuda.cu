@@ -3,7 +3,10 @@
 // library: without a CUDA device every entry point fails with PHOS_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -451,6 +454,41 @@ int phos_cuda_timer_end(phos_ctx* ctx, float* out_ms) {
 }
 
 uint64_t phos_cuda_launch_count(phos_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// Pin the calling thread (and the threads it spawns later) to the CPUs next to the GPU: page-locked ray arrays
+// are then first-touched on that NUMA node and the copy engines / zero-copy stores of phos_cuda_trace do not cross
+// the socket interconnect.  With 8 ranks on one box, unbound ranks share it and the host-pointer path drops to a
+// third of its single-GPU rate.  Returns the number of CPUs bound to, 0 when the topology is not exposed.
+int phos_cuda_bind_host_to_device(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return 0;
+  char line[4096] = {0};
+  const bool got = fgets(line, sizeof(line), f) != nullptr;
+  fclose(f);
+  if (!got) return 0;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int n = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k < 1) continue;
+    if (k == 1) b = a;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+      CPU_SET(c, &set);
+      ++n;
+    }
+  }
+  if (n == 0 || sched_setaffinity(0, sizeof(set), &set) != 0) return 0;
+  return n;
+}
 
 void* phos_cuda_host_alloc(uint64_t bytes) {
   void* p = nullptr;
