@@ -104,6 +104,13 @@ void        phos_bvh_free(phos_bvh* bvh);
 int phos_cuda_upload_accel(phos_ctx* ctx, const void* nodes288, uint32_t n_nodes, const void* packets384,
                            uint32_t n_packets);
 int phos_cuda_accel_stats(phos_ctx* ctx, phos_accel_stats* out);
+/* The packed structure built ON the device straight from the scene's triangles (no reference tree involved): Morton
+ * order, binary radix tree, collapse to the same 8-wide quantised layout.  Milliseconds instead of the seconds of the
+ * host build (bvh::from, src/accel/bvh/binned_sah_builder.hpp:215-281) + re-pack, at the price of a lower-quality
+ * tree (more node tests per ray).  Queries return the same hits; only exact ties in t between two triangles may
+ * resolve differently (tie-break = scene triangle order instead of the reference's packet order).
+ * In the stats, upload_seconds = flatten + copy the scene in, repack_seconds = the device build. */
+int phos_cuda_build_accel(phos_ctx* ctx, const phos_scene_desc* scene);
 
 /* ---- ray queries ----------------------------------------------------------------------------- */
 /* Trace n rays in place.  Per ray, exactly as the reference's trace(rays, active):

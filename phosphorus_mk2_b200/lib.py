@@ -73,6 +73,7 @@ SYMBOLS = {
     "phos_cuda_flush_l2": (_I, [_VP]),
     "phos_cuda_upload_scene": (_I, [_VP, C.POINTER(PhosSceneDesc)]),
     "phos_cuda_bind_host_to_device": (_I, [C.c_int]),
+    "phos_cuda_build_accel": (_I, [_VP, _VP]),
     "phos_cuda_camera_rays": (_I, [_VP, C.POINTER(PhosTile), _U32, C.c_float, C.c_float, _RP]),
     "phos_cuda_camera_rays_lens": (_I, [_VP, C.POINTER(PhosTile), _U32, C.c_float, C.c_float, C.c_uint64, _U32, _RP]),
     "phos_cuda_render": (_I, [_VP, C.POINTER(PhosTile), _U32, _U32, _U32, _U32, _U64]),
