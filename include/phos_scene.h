@@ -33,7 +33,7 @@ enum {
 /* Closure ids = bsdf_t::type_t (src/bsdf.hpp:14-24).  `param`: oren_nayar sigma in degrees
  * (bsdf/params.hpp:31-42), microfacet xalpha = yalpha BEFORE precompute (the glossy node passes roughness^2),
  * reflection / refraction eta, sheen roughness; unused otherwise.  Microfacet is the GGX reflection lobe
- * (refract = 0); the rough-refraction variant is not part of this subset. */
+ * (refract = 0), MICROFACET_REFRACT the GGX transmission lobe (src/bsdf/microfacet.hpp:36-172). */
 enum {
   PHOS_LOBE_DIFFUSE     = 1,
   PHOS_LOBE_OREN_NAYAR  = 2,
@@ -41,7 +41,10 @@ enum {
   PHOS_LOBE_REFRACTION  = 8,
   PHOS_LOBE_MICROFACET  = 16,
   PHOS_LOBE_SHEEN       = 32,
-  PHOS_LOBE_TRANSPARENT = 128
+  PHOS_LOBE_TRANSPARENT = 128,
+  PHOS_LOBE_MICROFACET_REFRACT = 16 | 256 /* bsdf_t::Microfacet with microfacet_t::refract = 1 (rough glass,
+                                             refraction_bsdf_node.osl:37): param = xalpha = yalpha before precompute
+                                             (the node passes roughness, not its square), param2 = eta */
 };
 #define PHOS_MAX_LOBES 8 /* bsdf_t::MaxLobes */
 
@@ -49,6 +52,7 @@ typedef struct phos_lobe {
   uint32_t type;      /* PHOS_LOBE_*            */
   float    weight[3]; /* closure weight (color) */
   float    param;
+  float    param2;    /* second parameter (eta of the rough-refraction lobe), 0 otherwise */
 } phos_lobe;
 
 typedef struct phos_material {

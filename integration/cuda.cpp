@@ -30,7 +30,7 @@
 // ShadingSystem::getattribute query on the shader group; the table-driven stand-in answers directly.
 bool material_builtin_closure(const material_t* m, uint32_t* kind, float cs[3], float* roughness, float* power);
 // ... and, for a material whose shader group flattens to a list of closures (mix / add trees): that list
-int material_builtin_lobes(const material_t* m, uint32_t* type, float* weight3, float* param);
+int material_builtin_lobes(const material_t* m, uint32_t* type, float* weight3, float* param, float* param2);
 
 namespace {
 
@@ -106,12 +106,13 @@ void flatten(const scene_t& scene, flat_scene_t& f) {
       throw std::runtime_error("cuda_t: material outside the built-in closure set");
     if (pm.kind == PHOS_MAT_LAYERED) {
       uint32_t type[PHOS_MAX_LOBES];
-      float weight[3 * PHOS_MAX_LOBES], param[PHOS_MAX_LOBES];
-      pm.num_lobes = (uint32_t)material_builtin_lobes(scene.material(i), type, weight, param);
+      float weight[3 * PHOS_MAX_LOBES], param[PHOS_MAX_LOBES], param2[PHOS_MAX_LOBES];
+      pm.num_lobes = (uint32_t)material_builtin_lobes(scene.material(i), type, weight, param, param2);
       for (uint32_t k = 0; k < pm.num_lobes; ++k) {
         pm.lobes[k].type = type[k];
         for (int c = 0; c < 3; ++c) pm.lobes[k].weight[c] = weight[3 * k + c];
         pm.lobes[k].param = param[k];
+        pm.lobes[k].param2 = param2[k];
       }
     }
     f.materials.push_back(pm);

@@ -109,7 +109,7 @@ void orc_film_jitter(uint32_t seed, uint32_t spp, float* jx, float* jy) {
 /* one lobe of bsdf_t after add_lobe + precompute (bsdf.hpp:52-83, bsdf/params.hpp): p0 / p1 = GGX alpha_x / alpha_y,
  * Oren-Nayar a / b, eta (reflection, refraction), sheen r */
 enum { BSDF_DIFFUSE_F = 1, BSDF_GLOSSY_F = 2, BSDF_SPECULAR_F = 4, BSDF_REFLECT_F = 8, BSDF_TRANSMIT_F = 16 };
-typedef struct { uint32_t type, flags; v3 w; float p0, p1; } lobe1;
+typedef struct { uint32_t type, flags; v3 w; float p0, p1, p2; } lobe1; /* p2: eta of the GGX transmission lobe */
 typedef struct bsdf1 { uint32_t n; lobe1 l[PHOS_MAX_LOBES]; } bsdf1;
 typedef struct {
   const phos_scene_desc* d;
@@ -135,13 +135,18 @@ static float roughness_to_alpha(float roughness) {
 }
 
 /* bsdf_t::add_lobe + T::precompute for one closure */
-static void add_lobe(bsdf1* b, uint32_t type, const float w[3], float param) {
+static void add_lobe(bsdf1* b, uint32_t type, const float w[3], float param, float param2) {
   if (b->n >= PHOS_MAX_LOBES) return;
   lobe1* l = &b->l[b->n++];
   l->type = type;
   l->w = V(w[0], w[1], w[2]);
-  l->p0 = l->p1 = 0.0f;
+  l->p0 = l->p1 = l->p2 = 0.0f;
   switch (type) {
+    case PHOS_LOBE_MICROFACET_REFRACT: /* add_lobe<microfacet_t> with refract = 1: flags = TRANSMIT (bsdf.hpp:69-83) */
+      l->flags = BSDF_TRANSMIT_F;
+      l->p0 = l->p1 = fminf(1.0f, fmaxf(0.0001f, roughness_to_alpha(param)));
+      l->p2 = param2;
+      break;
     case PHOS_LOBE_DIFFUSE: l->flags = BSDF_REFLECT_F | BSDF_DIFFUSE_F; break;
     case PHOS_LOBE_OREN_NAYAR: { /* oren_nayar_t::precompute, params.hpp:37-42 */
       l->flags = BSDF_REFLECT_F | BSDF_DIFFUSE_F;
@@ -173,12 +178,12 @@ void* orc_scene_create(const phos_scene_desc* d) {
     const float one[3] = {1.0f * mt->cs[0], 1.0f * mt->cs[1], 1.0f * mt->cs[2]}; /* w * component->w, w = (1,1,1) */
     switch (mt->kind) {
       case PHOS_MAT_DIFFUSE: /* diffuse_bsdf_node.osl:20-25 */
-        if (mt->roughness == 0) add_lobe(&s->bsdf[m], PHOS_LOBE_DIFFUSE, one, 0.0f);
-        else add_lobe(&s->bsdf[m], PHOS_LOBE_OREN_NAYAR, one, mt->roughness);
+        if (mt->roughness == 0) add_lobe(&s->bsdf[m], PHOS_LOBE_DIFFUSE, one, 0.0f, 0.0f);
+        else add_lobe(&s->bsdf[m], PHOS_LOBE_OREN_NAYAR, one, mt->roughness, 0.0f);
         break;
       case PHOS_MAT_GLOSSY: /* glossy_bsdf_node.osl:26-34 */
-        if (mt->roughness == 0.0f) add_lobe(&s->bsdf[m], PHOS_LOBE_REFLECTION, one, 0.0f);
-        else add_lobe(&s->bsdf[m], PHOS_LOBE_MICROFACET, one, mt->roughness * mt->roughness);
+        if (mt->roughness == 0.0f) add_lobe(&s->bsdf[m], PHOS_LOBE_REFLECTION, one, 0.0f, 0.0f);
+        else add_lobe(&s->bsdf[m], PHOS_LOBE_MICROFACET, one, mt->roughness * mt->roughness, 0.0f);
         break;
       case PHOS_MAT_EMITTER: { /* diffuse_emitter_node.osl:18 */
         const float k = (float)(mt->power / M_PI);
@@ -190,7 +195,7 @@ void* orc_scene_create(const phos_scene_desc* d) {
         break;
       case PHOS_MAT_LAYERED:
         for (uint32_t k = 0; k < mt->num_lobes && k < PHOS_MAX_LOBES; ++k)
-          add_lobe(&s->bsdf[m], mt->lobes[k].type, mt->lobes[k].weight, mt->lobes[k].param);
+          add_lobe(&s->bsdf[m], mt->lobes[k].type, mt->lobes[k].weight, mt->lobes[k].param, mt->lobes[k].param2);
         break;
       default: break;
     }
@@ -441,6 +446,61 @@ static float ct_pdf(v3 n, float ax, float ay, v3 wi, v3 wo) {
   const v3 wh = normalized(add(li, lo));
   return (ggx_D(ax, ay, wh) * ggx_G1(ax, ay, wi) * fabsf(dot(li, wh)) / fabsf(li.y)) / (4.0f * dot(li, wh));
 }
+/* cook_torrance::refract::{f, pdf, sample}, microfacet.hpp:36-172 (GGX transmission), to the letter: pdf divides by
+ * sqrt_denom and multiplies by it again (:113), and tests the hemisphere on the WORLD-space vectors (:108) */
+static float ctr_f(v3 n, float ax, float ay, float peta, v3 wi, v3 wo) {
+  const base_t base = make_base(n);
+  const v3 li = to_local(&base, wi), lo = to_local(&base, wo);
+  if ((li.y * lo.y) > 0.0f) return 0.0f;
+  const float eta = li.y > 0.0f ? peta : 1.0f / peta;
+  const float cos_ti = li.y, cos_to = lo.y;
+  if (cos_ti == 0.0f || cos_to == 0.0f) return 0.0f;
+  v3 wh = normalized(add(li, scl(lo, eta)));
+  if (wh.y < 0) wh = neg(wh);
+  if (dot(lo, wh) * dot(li, wh) > 0) return 0.0f;
+  const float f = fresnel_dielectric(dot(lo, wh), eta);
+  const float sqrt_denom = dot(li, wh) + eta * dot(lo, wh);
+  const float factor = 1.0f / eta;
+  const float d = ggx_D(ax, ay, wh);
+  const float g = 1.0f / (1.0f + ggx_Lambda(ax, ay, li) + ggx_Lambda(ax, ay, lo));
+  return (1.0f - f) * fabsf(d * g * eta * eta * fabsf(dot(lo, wh)) * fabsf(dot(li, wh)) * factor * factor /
+                            (cos_ti * cos_to * sqrt_denom * sqrt_denom));
+}
+static float ctr_pdf(v3 n, float ax, float ay, float peta, v3 wi, v3 wo) {
+  const base_t base = make_base(n);
+  const v3 li = to_local(&base, wi), lo = to_local(&base, wo);
+  const float eta = li.y > 0.0f ? peta : 1.0f / peta;
+  if (dot(wo, wi) > 0.0) return 0;
+  const v3 wh = normalized(add(li, scl(lo, eta)));
+  const float sqrt_denom = dot(li, wh) + eta * dot(lo, wh);
+  const float dwh_dwi = fabsf(eta * eta * dot(lo, wh)) / sqrt_denom * sqrt_denom;
+  return (ggx_D(ax, ay, wh) * wh.y) * dwh_dwi;
+}
+static float ctr_sample(v3 n, float ax, float ay, float peta, v3 wi, v3* wo, float u, float v, float* opdf) {
+  if (peta == 1.0f) {
+    *wo = neg(wi);
+    *opdf = 1.0f;
+    return 1.0f;
+  }
+  const base_t base = make_base(n);
+  const v3 li = to_local(&base, wi);
+  if (li.y == 0.0f) return 0.0f;
+  float dpdf;
+  const v3 wh = ggx_sample(ax, ay, li, &dpdf, u, v);
+  if (dot(wh, li) < 0.0f) return 0.0f;
+  const float eta = li.y > 0.0f ? 1.0f / peta : peta;
+  const float cos_ti = dot(wh, li);
+  const float sin2_ti = fmaxf(0.0f, 1.0f - cos_ti * cos_ti);
+  const float sin2_tt = eta * eta * sin2_ti;
+  if (sin2_tt >= 1.0f) return 0.0f;
+  const float cos_tt = sqrtf(1.0f - sin2_tt);
+  const v3 lo = add(scl(neg(li), eta), scl(wh, eta * cos_ti - cos_tt));
+  const float sqrt_denom = dot(li, wh) + eta * dot(lo, wh);
+  const float dwh_dwi = fabsf((eta * eta * dot(lo, wh)) / (sqrt_denom * sqrt_denom));
+  *opdf = dpdf * dwh_dwi;
+  *wo = to_world(&base, lo);
+  return ctr_f(n, ax, ay, peta, wi, *wo);
+}
 /* sample::hemisphere::cosine_weighted + orthogonal_base_t::to_world (math/sampling.hpp:23-36) */
 static v3 cosine_sample(v3 n, float sx, float sy, float* pdf) {
   const base_t base = make_base(n);
@@ -458,6 +518,7 @@ static float lobe_eval(const lobe1* l, v3 n, v3 wi, v3 wo, float* pdf) {
     case PHOS_LOBE_OREN_NAYAR: *pdf = (float)(dot(n, wi) * M_1_PI); return oren_nayar_f(n, l->p0, l->p1, wi, wo);
     case PHOS_LOBE_MICROFACET: *pdf = ct_pdf(n, l->p0, l->p1, wi, wo); return ct_f(n, l->p0, l->p1, wi, wo);
     case PHOS_LOBE_SHEEN: *pdf = (float)(dot(n, wi) * M_1_PI); return sheen_f(n, l->p0, wi, wo);
+    case PHOS_LOBE_MICROFACET_REFRACT: *pdf = ctr_pdf(n, l->p0, l->p1, l->p2, wi, wo); return ctr_f(n, l->p0, l->p1, l->p2, wi, wo);
     default: *pdf = 0.0f; return 0.0f; /* Reflection, Refraction, Transparent */
   }
 }
@@ -491,6 +552,10 @@ static int bsdf_sample(const bsdf1* b, v3 n, float sx, float sy, v3 wi, v3* wo, 
       if (r == 0.0f) return 0;
       break;
     case PHOS_LOBE_SHEEN: *wo = cosine_sample(n, u, sy, &pdf); r = sheen_f(n, l->p0, wi, *wo); break;
+    case PHOS_LOBE_MICROFACET_REFRACT:
+      r = ctr_sample(n, l->p0, l->p1, l->p2, wi, wo, u, sy, &pdf);
+      if (r == 0.0f) return 0;
+      break;
     case PHOS_LOBE_REFLECTION: { /* reflection.hpp:8-21 */
       const float ct = dot(n, wi);
       pdf = 1.0f;

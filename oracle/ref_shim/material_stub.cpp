@@ -33,6 +33,7 @@ struct stub_lobe_t {
   int type = 0;  // bsdf_t::type_t
   Imath::Color3f weight = Imath::Color3f(1.0f);
   float param = 0.0f;
+  float param2 = 0.0f;
 };
 
 struct material_t::details_t {
@@ -49,7 +50,7 @@ struct material_t::details_t {
   bool emitter() const { return node == "diffuse_emitter_node"; }
 
   // one closure component -> bsdf_t::add_lobe, exactly the calls of eval_closure (src/material.cpp:251-301)
-  static void add(bsdf_t* bsdf, const Imath::V3f& n, int type, const Imath::Color3f& cw, float param) {
+  static void add(bsdf_t* bsdf, const Imath::V3f& n, int type, const Imath::Color3f& cw, float param, float param2 = 0.0f) {
     switch (type) {
       case bsdf_t::Diffuse: {
         bsdf::lobes::diffuse_t p;
@@ -90,6 +91,18 @@ struct material_t::details_t {
         bsdf->add_lobe(bsdf_t::Microfacet, cw, &p);
         break;
       }
+      case bsdf_t::Microfacet | 256: {  // microfacet(ggx, N, 0, r, r, eta, 1): refraction_bsdf_node.osl:37
+        bsdf::lobes::microfacet_t p;
+        p.distribution = bsdf::lobes::microfacet_t::GGX;
+        p.n = n;
+        p.u = Imath::V3f(0.0f);
+        p.xalpha = param;
+        p.yalpha = param;
+        p.eta = param2;
+        p.refract = 1;
+        bsdf->add_lobe(bsdf_t::Microfacet, cw, &p);
+        break;
+      }
       case bsdf_t::Sheen: {
         bsdf::lobes::sheen_t p;
         p.n = n;
@@ -124,7 +137,7 @@ struct material_t::details_t {
       }
     } else if (node == "layered_node") {
       if (result.bsdf)
-        for (int i = 0; i < num_lobes; ++i) add(result.bsdf, n, lobes[i].type, lobes[i].weight, lobes[i].param);
+        for (int i = 0; i < num_lobes; ++i) add(result.bsdf, n, lobes[i].type, lobes[i].weight, lobes[i].param, lobes[i].param2);
     } else {  // diffuse_bsdf_node.osl:20-25: roughness 0 -> diffuse(N), else oren_nayar(N, roughness)
       if (result.bsdf) {
         if (roughness == 0.0f) add(result.bsdf, n, bsdf_t::Diffuse, Imath::Color3f(1.0f) * cs, 0.0f);
@@ -155,6 +168,7 @@ struct stub_builder_t : public material_t::builder_t {
     int k;
     std::string field;
     if (lobe_field(name, &k, &field) && field == "param") material->details->lobes[k].param = f;
+    if (lobe_field(name, &k, &field) && field == "param2") material->details->lobes[k].param2 = f;
   }
   void parameter(const std::string& name, int v) override {
     int k;
@@ -225,7 +239,7 @@ bool material_builtin_closure(const material_t* m, uint32_t* kind, float cs[3], 
 }
 
 // the closure list of a layered_node (kind 4 above): type / weight / param per lobe; returns the count
-int material_builtin_lobes(const material_t* m, uint32_t* type, float* weight3, float* param) {
+int material_builtin_lobes(const material_t* m, uint32_t* type, float* weight3, float* param, float* param2) {
   const auto* d = m->details;
   for (int i = 0; i < d->num_lobes; ++i) {
     type[i] = (uint32_t)d->lobes[i].type;
@@ -233,6 +247,7 @@ int material_builtin_lobes(const material_t* m, uint32_t* type, float* weight3, 
     weight3[3 * i + 1] = d->lobes[i].weight.y;
     weight3[3 * i + 2] = d->lobes[i].weight.z;
     param[i] = d->lobes[i].param;
+    param2[i] = d->lobes[i].param2;
   }
   return d->num_lobes;
 }

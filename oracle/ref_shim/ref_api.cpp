@@ -58,6 +58,7 @@ void fill_scene(scene_t& scene, const phos_scene_desc* d) {
       b->parameter(p + "type", (int)m.lobes[k].type);
       b->parameter(p + "weight", Imath::Color3f(m.lobes[k].weight[0], m.lobes[k].weight[1], m.lobes[k].weight[2]));
       b->parameter(p + "param", m.lobes[k].param);
+      b->parameter(p + "param2", m.lobes[k].param2);
     }
     scene.add("material" + std::to_string(i), mat);
   }

@@ -24,7 +24,7 @@ import threading
 import numpy as np
 
 from . import scenes
-from .scene import (LOBE_DIFFUSE, LOBE_MICROFACET, LOBE_OREN_NAYAR, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_SHEEN,
+from .scene import (LOBE_DIFFUSE, LOBE_MICROFACET, LOBE_MICROFACET_REFRACT, LOBE_OREN_NAYAR, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_SHEEN,
                     LOBE_TRANSPARENT, MAT_BACKGROUND, MAT_DIFFUSE, MAT_EMITTER, MAT_GLOSSY, MAT_LAYERED, MAX_LOBES, Camera,
                     Material, Mesh, Scene)
 
@@ -51,7 +51,7 @@ def _param(p):
 
 def _scale(lobes, k):
     k = np.float32(k)
-    return [(t, tuple(float(k * np.float32(c)) for c in w), prm) for (t, w, prm) in lobes]
+    return [(l[0], tuple(float(k * np.float32(c)) for c in l[1])) + tuple(l[2:]) for l in lobes]
 
 
 def _layer_closures(node: str, prm: dict, inputs: dict):
@@ -69,7 +69,7 @@ def _layer_closures(node: str, prm: dict, inputs: dict):
     if node == "refraction_bsdf_node":  # refraction_bsdf_node.osl:30-38
         if dist == "sharp" or rough == 0.0:
             return "bsdf", [(LOBE_REFRACTION, cs, float(prm.get("IoR", 0.5)))]
-        raise SceneError("rough refraction (microfacet with refract = 1) is outside the built-in closure set")
+        return "bsdf", [(LOBE_MICROFACET_REFRACT, cs, rough, float(prm.get("IoR", 0.5)))]  # microfacet(dist, N, 0, r, r, eta, 1)
     if node == "sheen_bsdf_node":  # sheen_bsdf_node.osl
         return "bsdf", [(LOBE_SHEEN, cs, rough)]
     if node == "transparent_bsdf_node":  # transparent_bsdf.node.osl

@@ -77,7 +77,7 @@ enum { BSDF_DIFFUSE_F = 1, BSDF_GLOSSY_F = 2, BSDF_SPECULAR_F = 4, BSDF_REFLECT_
 struct DevLobe {
   uint32_t type, flags;
   float w[3];
-  float p0, p1;
+  float p0, p1, p2;  // p2: eta of the GGX transmission lobe
 };
 // What material_t::evaluate leaves in shading_result_t for a hit on this material: the closure list
 // eval_closure builds (material.cpp:218-305) and the emission.
@@ -344,6 +344,61 @@ PHOS_LOBE_FN float ct_pdf(v3 n, float ax, float ay, v3 wi, v3 wo) {
   const v3 wh = normalized(add(li, lo));
   return (ggx_D(ax, ay, wh) * ggx_G1(ax, ay, wi) * fabsf(dot(li, wh)) / fabsf(li.y)) / (4.0f * dot(li, wh));
 }
+// cook_torrance::refract::{f, pdf, sample}, microfacet.hpp:36-172 (GGX transmission), to the letter: pdf divides by
+// sqrt_denom and multiplies by it again (:113), and tests the hemisphere on the WORLD-space vectors (:108)
+PHOS_LOBE_FN float ctr_f(v3 n, float ax, float ay, float peta, v3 wi, v3 wo) {
+  const Base base = make_base(n);
+  const v3 li = to_local(base, wi), lo = to_local(base, wo);
+  if ((li.y * lo.y) > 0.0f) return 0.0f;
+  const float eta = li.y > 0.0f ? peta : 1.0f / peta;
+  const float cos_ti = li.y, cos_to = lo.y;
+  if (cos_ti == 0.0f || cos_to == 0.0f) return 0.0f;
+  v3 wh = normalized(add(li, scl(lo, eta)));
+  if (wh.y < 0) wh = neg(wh);
+  if (dot(lo, wh) * dot(li, wh) > 0) return 0.0f;
+  const float f = fresnel_dielectric(dot(lo, wh), eta);
+  const float sqrt_denom = dot(li, wh) + eta * dot(lo, wh);
+  const float factor = 1.0f / eta;
+  const float d = ggx_D(ax, ay, wh);
+  const float g = 1.0f / (1.0f + ggx_Lambda(ax, ay, li) + ggx_Lambda(ax, ay, lo));
+  return (1.0f - f) * fabsf(d * g * eta * eta * fabsf(dot(lo, wh)) * fabsf(dot(li, wh)) * factor * factor /
+                            (cos_ti * cos_to * sqrt_denom * sqrt_denom));
+}
+PHOS_LOBE_FN float ctr_pdf(v3 n, float ax, float ay, float peta, v3 wi, v3 wo) {
+  const Base base = make_base(n);
+  const v3 li = to_local(base, wi), lo = to_local(base, wo);
+  const float eta = li.y > 0.0f ? peta : 1.0f / peta;
+  if ((double)dot(wo, wi) > 0.0) return 0;
+  const v3 wh = normalized(add(li, scl(lo, eta)));
+  const float sqrt_denom = dot(li, wh) + eta * dot(lo, wh);
+  const float dwh_dwi = fabsf(eta * eta * dot(lo, wh)) / sqrt_denom * sqrt_denom;
+  return (ggx_D(ax, ay, wh) * wh.y) * dwh_dwi;
+}
+PHOS_LOBE_FN float ctr_sample(v3 n, float ax, float ay, float peta, v3 wi, v3& wo, float u, float v, float& opdf) {
+  if (peta == 1.0f) {
+    wo = neg(wi);
+    opdf = 1.0f;
+    return 1.0f;
+  }
+  const Base base = make_base(n);
+  const v3 li = to_local(base, wi);
+  if (li.y == 0.0f) return 0.0f;
+  float dpdf;
+  const v3 wh = ggx_sample(ax, ay, li, dpdf, u, v);
+  if (dot(wh, li) < 0.0f) return 0.0f;
+  const float eta = li.y > 0.0f ? 1.0f / peta : peta;
+  const float cos_ti = dot(wh, li);
+  const float sin2_ti = fmaxf(0.0f, 1.0f - cos_ti * cos_ti);
+  const float sin2_tt = eta * eta * sin2_ti;
+  if (sin2_tt >= 1.0f) return 0.0f;
+  const float cos_tt = sqrtf(1.0f - sin2_tt);
+  const v3 lo = add(scl(neg(li), eta), scl(wh, eta * cos_ti - cos_tt));
+  const float sqrt_denom = dot(li, wh) + eta * dot(lo, wh);
+  const float dwh_dwi = fabsf((eta * eta * dot(lo, wh)) / (sqrt_denom * sqrt_denom));
+  opdf = dpdf * dwh_dwi;
+  wo = to_world(base, lo);
+  return ctr_f(n, ax, ay, peta, wi, wo);
+}
 // sample::hemisphere::cosine_weighted + orthogonal_base_t::to_world (math/sampling.hpp:23-36, lambert.hpp:24-36)
 PHOS_LOBE_FN v3 cosine_sample(v3 n, float sx, float sy, float& pdf) {
   const Base base = make_base(n);
@@ -361,6 +416,7 @@ __device__ __forceinline__ float lobe_eval(const DevLobe& l, v3 n, v3 wi, v3 wo,
     case 2: pdf = (float)(dot(n, wi) * PHOS_1_PI); return oren_nayar_f(n, l.p0, l.p1, wi, wo);     // OrenNayar
     case 16: pdf = ct_pdf(n, l.p0, l.p1, wi, wo); return ct_f(n, l.p0, l.p1, wi, wo);              // Microfacet (GGX)
     case 32: pdf = (float)(dot(n, wi) * PHOS_1_PI); return sheen_f(n, l.p0, wi, wo);               // Sheen
+    case 272: pdf = ctr_pdf(n, l.p0, l.p1, l.p2, wi, wo); return ctr_f(n, l.p0, l.p1, l.p2, wi, wo);  // Microfacet, refract = 1
     default: pdf = 0.0f; return 0.0f;                                                               // Reflection, Refraction, Transparent
   }
 }
@@ -398,6 +454,10 @@ __device__ __forceinline__ bool bsdf_sample(const DevMaterial* __restrict__ m, v
       if (r == 0.0f) return false;
       break;
     case 32: wo = cosine_sample(n, u, sy, pdf); r = sheen_f(n, l.p0, wi, wo); break;
+    case 272:
+      r = ctr_sample(n, l.p0, l.p1, l.p2, wi, wo, u, sy, pdf);
+      if (r == 0.0f) return false;
+      break;
     case 4: {  // reflection.hpp:8-21
       const float ct = dot(n, wi);
       pdf = 1.0f;

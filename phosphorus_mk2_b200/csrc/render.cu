@@ -182,13 +182,18 @@ int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
   std::vector<DevMaterial> mats(std::max<uint32_t>(1, d->num_materials));
   memset(mats.data(), 0, mats.size() * sizeof(DevMaterial));
   // bsdf_t::add_lobe + T::precompute for one closure (bsdf.hpp:52-83, bsdf/params.hpp)
-  auto add_lobe = [&](DevMaterial& o, uint32_t type, const float* w, float param) -> bool {
+  auto add_lobe = [&](DevMaterial& o, uint32_t type, const float* w, float param, float param2 = 0.0f) -> bool {
     if (o.nlobes >= PHOS_MAX_LOBES) return false;
     DevLobe& l = o.lobes[o.nlobes++];
     l.type = type;
     for (int c = 0; c < 3; ++c) l.w[c] = w[c];
-    l.p0 = l.p1 = 0.0f;
+    l.p0 = l.p1 = l.p2 = 0.0f;
     switch (type) {
+      case PHOS_LOBE_MICROFACET_REFRACT:  // add_lobe<microfacet_t> with refract = 1: flags = TRANSMIT
+        l.flags = BSDF_TRANSMIT_F;
+        l.p0 = l.p1 = std::min(1.0f, std::max(0.0001f, roughness_to_alpha(param)));
+        l.p2 = param2;
+        return param2 != 0.0f;  // eta 0 divides by zero in the reference as well
       case PHOS_LOBE_DIFFUSE: l.flags = BSDF_REFLECT_F | BSDF_DIFFUSE_F; return true;
       case PHOS_LOBE_OREN_NAYAR: {  // oren_nayar_t::precompute, params.hpp:37-42
         l.flags = BSDF_REFLECT_F | BSDF_DIFFUSE_F;
@@ -233,7 +238,7 @@ int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
         break;
       case PHOS_MAT_LAYERED:
         if (in.num_lobes > PHOS_MAX_LOBES) return fail(ctx, PHOS_ERR_INVALID, "more than 8 closures in one material (bsdf_t::MaxLobes)");
-        for (uint32_t k = 0; ok && k < in.num_lobes; ++k) ok = add_lobe(o, in.lobes[k].type, in.lobes[k].weight, in.lobes[k].param);
+        for (uint32_t k = 0; ok && k < in.num_lobes; ++k) ok = add_lobe(o, in.lobes[k].type, in.lobes[k].weight, in.lobes[k].param, in.lobes[k].param2);
         break;
       default: ok = false;
     }

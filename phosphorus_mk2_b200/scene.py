@@ -17,11 +17,12 @@ import numpy as np
 MAT_DIFFUSE, MAT_GLOSSY, MAT_EMITTER, MAT_BACKGROUND, MAT_LAYERED = 0, 1, 2, 3, 4
 # closure ids = bsdf_t::type_t (src/bsdf.hpp:14-24)
 LOBE_DIFFUSE, LOBE_OREN_NAYAR, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_MICROFACET, LOBE_SHEEN, LOBE_TRANSPARENT = 1, 2, 4, 8, 16, 32, 128
+LOBE_MICROFACET_REFRACT = 16 | 256  # GGX transmission (rough glass): (type, weight, roughness, eta)
 MAX_LOBES = 8
 
 
 class PhosLobe(C.Structure):
-    _fields_ = [("type", C.c_uint32), ("weight", C.c_float * 3), ("param", C.c_float)]
+    _fields_ = [("type", C.c_uint32), ("weight", C.c_float * 3), ("param", C.c_float), ("param2", C.c_float)]
 
 
 class PhosMaterial(C.Structure):
@@ -79,8 +80,9 @@ class Material:
         tree (src/material.cpp:218-305): A's closures first with weights * (1 - fac), then B's * fac."""
         out = []
         for m, k in ((a, np.float32(1.0) - np.float32(fac)), (b, np.float32(fac))):
-            for (t, w, prm) in m.closures():
-                out.append((t, tuple(float(np.float32(k) * np.float32(c)) for c in w), prm))
+            for lobe in m.closures():
+                t, w = lobe[0], lobe[1]
+                out.append((t, tuple(float(np.float32(k) * np.float32(c)) for c in w)) + tuple(lobe[2:]))
         assert len(out) <= MAX_LOBES
         return Material(MAT_LAYERED, lobes=tuple(out))
 
@@ -209,10 +211,12 @@ class Scene:
             mats[i].roughness = m.roughness
             mats[i].power = m.power
             mats[i].num_lobes = len(m.lobes)
-            for k, (t, w, prm) in enumerate(m.lobes):
+            for k, lobe in enumerate(m.lobes):
+                t, w, prm = lobe[:3]
                 mats[i].lobes[k].type = t
                 mats[i].lobes[k].weight = (C.c_float * 3)(*w)
                 mats[i].lobes[k].param = prm
+                mats[i].lobes[k].param2 = lobe[3] if len(lobe) > 3 else 0.0
 
         def p(a, t):
             return a.ctypes.data_as(C.POINTER(t)) if a is not None else C.POINTER(t)()

@@ -35,6 +35,18 @@ def test_yaml_scene_is_imported_like_the_reference_codec():
     assert d.environment == 4 and d.materials[1].num_lobes == 2
 
 
+def test_refraction_node_sharp_and_rough():
+    from phosphorus_mk2_b200.scene import LOBE_MICROFACET_REFRACT, LOBE_REFRACTION
+    def mat(params):
+        return codec.material_from_yaml({"shaders": [{"name": "refraction_bsdf_node", "layer": "l0", "parameters": params}]})
+    ior = {"name": "IoR", "type": "float", "value": 1.5}
+    assert mat([ior]).lobes == ((LOBE_REFRACTION, (1.0, 1.0, 1.0), 1.5),)
+    rough = mat([ior, {"name": "roughness", "type": "float", "value": 0.2}])
+    assert rough.lobes == ((LOBE_MICROFACET_REFRACT, (1.0, 1.0, 1.0), 0.2, 1.5),)  # roughness, not its square (osl:31)
+    sharp = mat([ior, {"name": "roughness", "type": "float", "value": 0.2}, {"name": "distribution", "type": "string", "value": "sharp"}])
+    assert sharp.lobes[0][0] == LOBE_REFRACTION
+
+
 def test_unknown_nodes_and_importers_are_rejected(tmp_path):
     bad = tmp_path / "bad.yaml"
     bad.write_text("materials:\n  m:\n    shaders:\n      - {name: principled_bsdf_node, layer: l0}\ndata:\n  - {generator: cornell_box}\n")

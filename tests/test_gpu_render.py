@@ -63,13 +63,14 @@ def test_wider_closure_set_matches_oracle(oracle, depth, spp):
     assert got[..., :3].mean() > got_dark[..., :3].mean() * 1.02  # the environment is seen through the open front
 
 
-@pytest.mark.parametrize("lobe", ["oren_nayar", "mirror", "glass", "sheen", "transparent"])
+@pytest.mark.parametrize("lobe", ["oren_nayar", "mirror", "glass", "rough_glass", "sheen", "transparent"])
 def test_single_closures_match_oracle(oracle, lobe):
-    from phosphorus_mk2_b200.scene import LOBE_REFRACTION, LOBE_SHEEN, LOBE_TRANSPARENT, MAT_LAYERED, Material
+    from phosphorus_mk2_b200.scene import LOBE_MICROFACET_REFRACT, LOBE_REFRACTION, LOBE_SHEEN, LOBE_TRANSPARENT, MAT_LAYERED, Material
     sc = scenes.cornell_box(48, 48)
     new = {"oren_nayar": Material(MAT_DIFFUSE, (0.7, 0.6, 0.5), roughness=30.0),
            "mirror": Material(MAT_GLOSSY, (0.9, 0.9, 0.9), roughness=0.0),
            "glass": Material(MAT_LAYERED, lobes=((LOBE_REFRACTION, (0.95, 0.95, 0.95), 1.45),)),
+           "rough_glass": Material(MAT_LAYERED, lobes=((LOBE_MICROFACET_REFRACT, (0.95, 0.95, 0.95), 0.3, 1.45),)),
            "sheen": Material(MAT_LAYERED, lobes=((LOBE_SHEEN, (0.8, 0.7, 0.9), 0.5),)),
            "transparent": Material(MAT_LAYERED, lobes=((LOBE_TRANSPARENT, (0.8, 0.9, 0.8), 0.0),))}[lobe]
     sc.materials[3] = new  # the tall box

@@ -108,8 +108,9 @@ def test_camera_rays_against_the_compiled_reference_kernel(oracle, reflib, apert
 
 
 def _lobe_materials():
-    from phosphorus_mk2_b200.scene import (LOBE_DIFFUSE, LOBE_MICROFACET, LOBE_OREN_NAYAR, LOBE_REFLECTION, LOBE_REFRACTION,
-                                           LOBE_SHEEN, LOBE_TRANSPARENT, MAT_DIFFUSE, MAT_GLOSSY, MAT_LAYERED, Material)
+    from phosphorus_mk2_b200.scene import (LOBE_DIFFUSE, LOBE_MICROFACET, LOBE_MICROFACET_REFRACT, LOBE_OREN_NAYAR, LOBE_REFLECTION,
+                                           LOBE_REFRACTION, LOBE_SHEEN, LOBE_TRANSPARENT, MAT_DIFFUSE, MAT_GLOSSY, MAT_LAYERED,
+                                           Material)
     grey, red = (0.7, 0.7, 0.7), (0.8, 0.2, 0.1)
     return [
         Material(MAT_DIFFUSE, grey),                                   # diffuse(N)
@@ -123,6 +124,10 @@ def _lobe_materials():
         Material.mix(Material(MAT_DIFFUSE, grey, roughness=15.0), Material(MAT_LAYERED, lobes=((LOBE_SHEEN, red, 0.4),)), 0.3),
         Material(MAT_LAYERED, lobes=((LOBE_DIFFUSE, grey, 0.0), (LOBE_REFLECTION, red, 0.0), (LOBE_REFRACTION, grey, 1.3),
                                      (LOBE_MICROFACET, grey, 0.09), (LOBE_TRANSPARENT, red, 0.0))),
+        Material(MAT_LAYERED, lobes=((LOBE_MICROFACET_REFRACT, grey, 0.3, 1.5),)),  # rough glass: microfacet(ggx, N, 0, r, r, eta, 1)
+        Material(MAT_LAYERED, lobes=((LOBE_MICROFACET_REFRACT, red, 0.15, 1.0),)),  # eta == 1: passes straight through
+        Material.mix(Material(MAT_LAYERED, lobes=((LOBE_MICROFACET_REFRACT, grey, 0.4, 1.33),)),
+                     Material(MAT_LAYERED, lobes=((LOBE_REFRACTION, red, 1.33), (LOBE_TRANSPARENT, grey, 0.0))), 0.5),
     ]
 
 
