@@ -10,13 +10,18 @@
 //     (ballot + popc ranks, no atomics), so a long ray never holds 31 finished lanes hostage;
 //   * warp-voted phases: two ballots per iteration say what every lane wants next; the warp then runs
 //     either one node step (8 quantised child boxes, ~245 instructions) for the lanes that need one,
-//     or one Möller–Trumbore step (~60 instructions) for the lanes with pending leaf triangles — the
+//     or one triangle step (up to two Möller–Trumbore tests of the open leaf piece, both 48-byte
+//     fetches in flight together, ~150 instructions) for the lanes with pending leaf triangles — the
 //     vote is weighted towards the cheaper triangle step — so both inner loops run converged instead
 //     of every lane dragging the warp through its own leaf loop;
-//   * traversal stack: kSmemStack entries per ray in shared memory ([entry][thread], conflict-free),
-//     deeper entries in a local-memory spill that ordinary trees never touch.
+//   * hit record = the index of the triangle held so far; its ids (and, on an exact tie in t only, its
+//     tie-break order) are read back from the packed triangle when needed: three registers fewer;
+//   * traversal stack: kSmemStack entries per ray in shared memory ([entry][thread], conflict-free,
+//     stack pointer in a register), deeper entries in a local-memory spill that ordinary trees never
+//     touch.
 // Measured alternatives that did not pay off (profiles/r01_summary.md): L1 prefetch of the next node,
-// 64 registers / 8 CTAs per SM, sorting the ray stream, fused leaves.
+// 64 registers / 8 CTAs per SM, sorting the ray stream, fused leaves, other vote biases / refill
+// thresholds, packed FFMA2 plane evaluation.
 #pragma once
 #include "trace_ray.cuh"
 

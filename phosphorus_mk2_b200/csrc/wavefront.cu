@@ -5,8 +5,10 @@
 //   per bounce:     trace (closest hit)                                                 (trace.cuh)
 //                   shade_nee   interaction, closure, light sample -> shadow-ray queue  (deferred_shading_kernel.hpp,
 //                                                                                        spt.hpp:95-149)
+//                   [normals_channel: the NORMALS channel, first bounce only              (cpu.cpp:194-196)]
 //                   trace (any hit, the shadow queue)
-//                   integrate   radiance, Russian roulette, BSDF sample, and compaction
+//                   integrate   radiance (+ environment on a miss), Russian roulette, bsdf_t::sample
+//                               over the material's closure list, and compaction
 //                               of the survivors into the next ray stream with warp-
 //                               aggregated queue appends (ballot + popc + one atomic)    (spt.hpp:161-328)
 //   film_accumulate radiance / (spp * pps) into the device film                          (cpu.cpp:175-198)
