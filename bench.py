@@ -350,6 +350,27 @@ def main():
     result = drays.download()
     hits = int(result.hit.sum())
 
+    # ---- the same frame as occlusion queries (BASELINE metric "closest-hit, shadow"): any-hit Mrays/s ------------
+    # SHADOW set on every camera ray (tmax = FLT_MAX): the traversal stops at the first accepted triangle.  Rank 0.
+    any_hit = None
+    if rank == 0:
+        from phosphorus_mk2_b200.rays import SHADOW
+        dev.camera_rays(tiles, drays)
+        shadow_host = drays.download()
+        shadow_host.flags[:] = SHADOW
+        ms = []
+        for i in range(3 + max(3, min(args.steps, 10))):
+            dev.flush_l2()
+            drays.upload(shadow_host)
+            dev.timer_begin()
+            dev.trace_device(drays)
+            t = dev.timer_end()
+            if i >= 3:
+                ms.append(t)
+        occluded = drays.download()
+        any_hit = {"value": n / (float(np.mean(ms)) * 1e-3) / 1e6, "unit": "Mrays/s", "rays": n,
+                   "occluded_fraction": float(occluded.hit.mean()), "verdict_equals_closest_hit": bool(np.array_equal(occluded.hit, result.hit))}
+
     # ---- end to end through the C ABI with pinned host arrays: e2e ------------------------------------
     dev.camera_rays(tiles, drays)
     pristine = drays.download()
@@ -450,6 +471,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 8 * n + 16 * hits,
                         "steps": e2e_steps, "matches_device_path": e2e_ok, "host_cpus_bound": numa_cpus},
+                "any_hit": any_hit,
                 "roofline": roof, "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line), flush=True)
     dev.close()
