@@ -39,12 +39,10 @@ constexpr int kSpillStack = 80;   // further entries (local memory; only touched
 // relative slack of the distance cull: nodes are entered while t_near <= d * (1 + 2^-15), so a
 // triangle whose Möller–Trumbore distance undercuts the current best by rounding error is still seen
 #define PHOS_CULL_SLACK 1.000030517578125f /* 1 + 2^-15 */
-// Packed fp32 (Blackwell FFMA2 / FMUL2) for the plane evaluation: measured 1.5-2.5 % SLOWER than the scalar
-// form on the B200 (profiles/r01_sweep_ffma2.log: the register pairing costs more moves than the 28 issue
-// slots it saves), so it stays off; kept as a build knob.
-#ifndef PHOS_FFMA2
-#define PHOS_FFMA2 0
-#endif
+// Measured and dropped (profiles/): packed fp32 (FFMA2) plane evaluation, 1.5-2.5 % slower than scalar FFMA
+// (r01_sweep_ffma2.log); decoding some of the plane bytes off the ALU pipe — I2F.U8 on the XU pipe, or one PRMT into a
+// half2 of 1024 + q widened by two HADD2.F32 on the FMA pipe — no gain in any mix (r01_sweep_decode_forms.log): the
+// kernel is bound by the number of instructions issued, not by one pipe.
 
 struct Ray {
   float ox, oy, oz;
@@ -159,39 +157,25 @@ __device__ __forceinline__ NodeHits node_test(const DevAccel& A, uint32_t node, 
   const uint32_t fy0 = negy ? n2.z : n4.x, fy1 = negy ? n2.w : n4.y;
   const uint32_t nz0 = negz ? n4.z : n3.x, nz1 = negz ? n4.w : n3.y;
   const uint32_t fz0 = negz ? n3.x : n4.z, fz1 = negz ? n3.y : n4.w;
-  uint32_t hits = 0u;  // slot space
-#if PHOS_FFMA2
-  // Blackwell's packed fp32 pipe: one FFMA2 evaluates the same plane of two children (each half is an
-  // ordinary round-to-nearest fma, so the result is the scalar one, bit for bit) — 24 + 4 issue slots
-  // instead of 48 + 8 in a kernel that is issue bound.
-  const float2 s2x = make_float2(sx, sx), s2y = make_float2(sy, sy), s2z = make_float2(sz, sz);
-  const float2 b2x = make_float2(bx, bx), b2y = make_float2(by, by), b2z = make_float2(bz, bz);
-  const float2 slack2 = make_float2(PHOS_SLAB_SLACK, PHOS_SLAB_SLACK);
+  // A child is hit when max(tn, 0) <= min(tf, dmax) * slack, i.e. tn <= tf * slack and tn <= dmax * slack and tf >= 0
+  // (and dmax >= 0, which only matters for rays that can accept nothing).  Each condition is the SIGN of a value
+  // computed on the FMA pipe; one LOP3 ors the three signs and one funnel shift appends the bit: 4 ALU-pipe
+  // instructions per child instead of the 6.3 of the clamp / compare / select form (+4 % Mrays/s,
+  // profiles/r01_sweep_sign_hits.log).  A NaN (inf - inf) reads as "hit": conservative.
+  const float dms = dmax * PHOS_SLAB_SLACK;
+  uint32_t miss = 0u;
 #pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    const float2 tnx = __ffma2_rn(make_float2(qplane(nx0, nx1, i), qplane(nx0, nx1, i + 1)), s2x, b2x);
-    const float2 tfx = __ffma2_rn(make_float2(qplane(fx0, fx1, i), qplane(fx0, fx1, i + 1)), s2x, b2x);
-    const float2 tny = __ffma2_rn(make_float2(qplane(ny0, ny1, i), qplane(ny0, ny1, i + 1)), s2y, b2y);
-    const float2 tfy = __ffma2_rn(make_float2(qplane(fy0, fy1, i), qplane(fy0, fy1, i + 1)), s2y, b2y);
-    const float2 tnz = __ffma2_rn(make_float2(qplane(nz0, nz1, i), qplane(nz0, nz1, i + 1)), s2z, b2z);
-    const float2 tfz = __ffma2_rn(make_float2(qplane(fz0, fz1, i), qplane(fz0, fz1, i + 1)), s2z, b2z);
-    const float tn0 = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, 0.0f)), tn1 = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, 0.0f));
-    const float2 tf = __fmul2_rn(make_float2(fminf(fminf(tfx.x, tfy.x), fminf(tfz.x, dmax)), fminf(fminf(tfx.y, tfy.y), fminf(tfz.y, dmax))),
-                                 slack2);
-    hits |= (tn0 <= tf.x ? 1u : 0u) << i;
-    hits |= (tn1 <= tf.y ? 1u : 0u) << (i + 1);
-  }
-#else
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 7; i >= 0; --i) {
     const float tnx = __fmaf_rn(qplane(nx0, nx1, i), sx, bx), tfx = __fmaf_rn(qplane(fx0, fx1, i), sx, bx);
     const float tny = __fmaf_rn(qplane(ny0, ny1, i), sy, by), tfy = __fmaf_rn(qplane(fy0, fy1, i), sy, by);
     const float tnz = __fmaf_rn(qplane(nz0, nz1, i), sz, bz), tfz = __fmaf_rn(qplane(fz0, fz1, i), sz, bz);
-    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, dmax));
-    hits |= (tn <= tf * PHOS_SLAB_SLACK ? 1u : 0u) << i;
+    const float tn = fmaxf(fmaxf(tnx, tny), tnz);
+    const float tf = fminf(fminf(tfx, tfy), tfz);
+    const float a = __fmaf_rn(tf, PHOS_SLAB_SLACK, -tn);
+    const float b = __fsub_rn(dms, tn);
+    miss = __funnelshift_l(__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(tf), miss, 1);
   }
-#endif
+  const uint32_t hits = ~miss & 0xffu;  // slot space
   // slot space -> key space: bit i moves to bit i ^ oct (three conditional swaps)
   uint32_t both = (hits & h.imask) | ((hits & ~h.imask & 0xffu) << 8);
   if (rd.oct & 1u) both = ((both & 0x5555u) << 1) | ((both >> 1) & 0x5555u);

@@ -47,12 +47,14 @@ def emul():
     import ctypes as C
     from phosphorus_mk2_b200.rays import PhosRays
     here = os.path.join(ROOT, "tests", "emul")
-    so = os.path.join(here, "libemul_trace.so")
+    defs = os.environ.get("PHOS_EMUL_DEFS", "").split()  # e.g. "-DPHOS_SIGN_HITS=0": emulate a kernel build knob
+    tag = "".join(c if c.isalnum() else "_" for c in "".join(defs))
+    so = os.path.join(here, f"libemul_trace{tag}.so")
     srcs = [os.path.join(here, "emul_trace.cpp"), os.path.join(ROOT, "phosphorus_mk2_b200", "csrc", "repack.cpp")]
     deps = srcs + [os.path.join(ROOT, "phosphorus_mk2_b200", "csrc", f) for f in ("trace_ray.cuh", "phos_internal.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-                        "-I/usr/local/cuda/include", *srcs, "-o", so], check=True)
+                        "-I/usr/local/cuda/include", *defs, *srcs, "-o", so], check=True)
     L = C.CDLL(so)
     L.emul_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(PhosRays), C.c_uint64,
                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_char_p]

@@ -13,6 +13,8 @@
 #include <string>
 
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { s &= 31u; return s ? (hi << s) | (lo >> (32u - s)) : hi; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
@@ -22,8 +24,6 @@ static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline uint4 __ldg(const uint4* p) { return *p; }
 static inline uint32_t __ldg(const uint32_t* p) { return *p; }
-static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
-static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
   const uint64_t t = ((uint64_t)y << 32) | x;
   uint32_t r = 0;
