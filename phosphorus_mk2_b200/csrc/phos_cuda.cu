@@ -130,8 +130,11 @@ int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t s
   for (int k = 0; k < 8; ++k) a.tma_ok &= ((uintptr_t)in_ptr(dev, k) & 15u) == 0;
   const uint64_t want = (n + (uint64_t)kChunk * kTraceWarps - 1) / ((uint64_t)kChunk * kTraceWarps);
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * ctx->trace_blocks_per_sm);
-  if (count) trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(a);
-  else trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(a);
+  // trees that fit the shared-memory stack (every re-grouped tree so far) run the instantiation without a spill tier
+  const bool deep = ctx->stats.max_depth + 2 > (uint32_t)kSmemStack;
+  if (count) trace_kernel<true, true><<<grid, kTraceBlock, 0, stream>>>(a);
+  else if (deep) trace_kernel<false, true><<<grid, kTraceBlock, 0, stream>>>(a);
+  else trace_kernel<false, false><<<grid, kTraceBlock, 0, stream>>>(a);
   ctx->launches++;
   if (!cuda_ok(ctx, cudaGetLastError(), "trace_kernel launch")) return PHOS_ERR_CUDA;
   return PHOS_OK;
@@ -187,7 +190,7 @@ phos_ctx* phos_cuda_create(int device, const phos_options* options) {
        cuda_ok(nullptr, cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long)), "cudaMalloc(counters)") &&
        cuda_ok(nullptr, cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long)), "cudaMemset(counters)");
   int blocks = 0;
-  ok = ok && cuda_ok(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, trace_kernel<false>, kTraceBlock, 0),
+  ok = ok && cuda_ok(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, trace_kernel<false, false>, kTraceBlock, 0),
                      "occupancy(trace_kernel)");
   if (!ok) {
     phos_cuda_destroy(ctx);

@@ -17,8 +17,8 @@
 //   * hit record = the index of the triangle held so far; its ids (and, on an exact tie in t only, its
 //     tie-break order) are read back from the packed triangle when needed: three registers fewer;
 //   * traversal stack: kSmemStack entries per ray in shared memory ([entry][thread], conflict-free,
-//     stack pointer in a register), deeper entries in a local-memory spill that ordinary trees never
-//     touch.
+//     stack pointer in a register); a second instantiation (kDeep) with a local-memory spill tier serves
+//     trees deeper than that (the re-grouped trees are 8-10 levels deep and never need it).
 // Measured alternatives that did not pay off (profiles/r01_summary.md): L1 prefetch of the next node,
 // 64 registers / 8 CTAs per SM, sorting the ray stream, fused leaves, other vote biases / refill
 // thresholds, packed FFMA2 plane evaluation.
@@ -81,7 +81,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   } while (!done);
 }
 
-template <bool kCount>
+// kDeep: the tree may be deeper than the shared-memory stack (upload knows the depth).  Only that instantiation
+// carries the local-memory spill tier; the common one has no stack-range checks at all in push / pop.
+template <bool kCount, bool kDeep>
 __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(const TraceArgs P) {
   __shared__ uint2 s_stack[kSmemStack * kTraceBlock];
   __shared__ alignas(128) uint32_t s_stage[kTraceWarps][2][8][kChunk];
@@ -160,16 +162,16 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   // deeper entries in a local array that ordinary trees never touch (the Stack struct of trace_ray.cuh
   // is the same thing for the one-ray loop; taking it apart here keeps sp out of local memory)
   uint2* const my_stack = s_stack + threadIdx.x;
-  uint2 spill[kSpillStack];
+  uint2 spill[kDeep ? kSpillStack : 1];
   int sp = 0;
   auto push = [&](uint2 v) {
-    if (sp < kSmemStack) my_stack[sp * kTraceBlock] = v;
+    if (!kDeep || sp < kSmemStack) my_stack[sp * kTraceBlock] = v;
     else if (sp < kSmemStack + kSpillStack) spill[sp - kSmemStack] = v;
     ++sp;
   };
   auto pop = [&]() -> uint2 {
     --sp;
-    return sp < kSmemStack ? my_stack[sp * kTraceBlock] : spill[sp - kSmemStack];
+    return (!kDeep || sp < kSmemStack) ? my_stack[sp * kTraceBlock] : spill[sp - kSmemStack];
   };
   Ray r;
   RayDir rd;
@@ -252,34 +254,36 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
         }
         if (lt >> 8) {
           const uint4* tp = P.accel.tris + 3ull * tptr;
-          const uint32_t tptr0 = tptr;
           const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
 #if PHOS_TRI_PAIR
-          // two triangles of the leaf per step: both 48-byte fetches are in flight together
+          // two triangles of the leaf per step: both 48-byte fetches are in flight together.  The second
+          // triangle's registers are left undefined (not copied from the first) when there is none.
           const bool two = lt >= 0x200u;
-          uint4 a2 = a, b2 = b, c2 = c;
+          uint4 a2, b2, c2;
+          asm("" : "=r"(a2.x), "=r"(a2.y), "=r"(a2.z), "=r"(a2.w));
+          asm("" : "=r"(b2.x), "=r"(b2.y), "=r"(b2.z), "=r"(b2.w));
+          asm("" : "=r"(c2.x), "=r"(c2.y), "=r"(c2.z), "=r"(c2.w));
           if (two) {
             a2 = __ldg(tp + 3);
             b2 = __ldg(tp + 4);
             c2 = __ldg(tp + 5);
           }
-          tptr += two ? 2u : 1u;
-          lt -= two ? 0x200u : 0x100u;
-          if (kCount) n_tris += two ? 2u : 1u;
 #else
           const bool two = false;
           const uint4 a2 = a, b2 = b, c2 = c;
-          ++tptr;
-          lt -= 0x100u;
-          if (kCount) ++n_tris;
 #endif
           float ds, us, vs;
           bool done = false;
-          if (mt_triangle(a, b, c, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) && accept_hit(P.accel, r, ds, us, vs, tptr0))
+          if (mt_triangle(a, b, c, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) && accept_hit(P.accel, r, ds, us, vs, tptr))
             done = (r.flags & PHOS_SHADOW) != 0u;
           if (two && !done && mt_triangle(a2, b2, c2, r.ox, r.oy, r.oz, r.wx, r.wy, r.wz, ds, us, vs) &&
-              accept_hit(P.accel, r, ds, us, vs, tptr0 + 1u))
+              accept_hit(P.accel, r, ds, us, vs, tptr + 1u))
             done = (r.flags & PHOS_SHADOW) != 0u;
+          // advance past what was tested (the pair flag is re-read from lt: nothing extra stays live over the tests)
+          const bool adv2 = PHOS_TRI_PAIR && lt >= 0x200u;
+          tptr += adv2 ? 2u : 1u;
+          lt -= adv2 ? 0x200u : 0x100u;
+          if (kCount) n_tris += adv2 ? 2u : 1u;
           if (done) {  // any-hit: this ray is finished
             lt = 0u;
             cur.y = 0u;

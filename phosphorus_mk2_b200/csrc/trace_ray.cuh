@@ -123,6 +123,17 @@ __device__ __forceinline__ float qplane(uint32_t w0, uint32_t w1, int i) {
   return __uint_as_float(__byte_perm(i < 4 ? w0 : w1, 0x3F800000u, 0x7604u + ((uint32_t)(i & 3) << 4)));
 }
 
+// (a & mask) | (b & ~mask) as ONE LOP3 (nvcc narrows the masks of the plain expression and emits two)
+__device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t mask) {
+#ifdef __CUDA_ARCH__
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(mask));
+  return d;
+#else
+  return (a & mask) | (b & ~mask);
+#endif
+}
+
 struct NodeHits {
   uint32_t inner;       // hit inner children, key space (key = slot ^ oct)
   uint32_t leaf;        // hit leaf children, key space
@@ -178,9 +189,9 @@ __device__ __forceinline__ NodeHits node_test(const DevAccel& A, uint32_t node, 
   const uint32_t hits = ~miss & 0xffu;  // slot space
   // slot space -> key space: bit i moves to bit i ^ oct (three conditional swaps)
   uint32_t both = (hits & h.imask) | ((hits & ~h.imask & 0xffu) << 8);
-  if (rd.oct & 1u) both = ((both & 0x5555u) << 1) | ((both >> 1) & 0x5555u);
-  if (rd.oct & 2u) both = ((both & 0x3333u) << 2) | ((both >> 2) & 0x3333u);
-  if (rd.oct & 4u) both = ((both & 0x0f0fu) << 4) | ((both >> 4) & 0x0f0fu);
+  if (rd.oct & 1u) both = bitselect(both << 1, both >> 1, 0xaaaaaaaau);
+  if (rd.oct & 2u) both = bitselect(both << 2, both >> 2, 0xccccccccu);
+  if (rd.oct & 4u) both = bitselect(both << 4, both >> 4, 0xf0f0f0f0u);
   h.inner = both & 0xffu;
   h.leaf = both >> 8;
   return h;
