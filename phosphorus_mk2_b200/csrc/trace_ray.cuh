@@ -24,6 +24,10 @@ namespace phos {
 struct DevAccel {
   const uint4* nodes;  // GNode, 5 x uint4 each
   const uint4* tris;   // GTri, 3 x uint4 each
+  // the bits of 1.0f, passed as a kernel parameter so that the plane decode is PRMT w, <selector immediate>,
+  // c[0x0][..]: with a constant ptxas can see, it sometimes flips to PRMT w, <selector register>, 0x3F800000 and
+  // spends 40 instructions per node materialising the eight selectors
+  uint32_t one = 0x3F800000u;
 };
 
 constexpr int kTraceBlock = 128;  // threads per CTA
@@ -59,9 +63,24 @@ constexpr uint32_t kNoTri = 0xffffffffu;
 
 // per-ray constants of the slab test
 struct RayDir {
-  float idx, idy, idz;  // 1 / dir (IEEE); a zero / tiny component is treated as +-2^-60
+  float idx, idy, idz;  // ~1 / dir; a zero / tiny component is treated as +-2^-60
   uint32_t oct;         // bit a set <=> dir[a] < 0
 };
+
+// 1 / x to 1 ulp (MUFU.RCP).  The reciprocal directions only feed the conservative box test: a relative error
+// e <= 2^-23 scales every plane distance of one axis by (1 + e), i.e. shifts near / far comparisons across axes by
+// <= 2 e — inside PHOS_SLAB_SLACK next to the ~10 * 2^-24 of the fma form, and far inside PHOS_CULL_SLACK.  Hit
+// records come from Möller–Trumbore alone, which never sees these values.  (An IEEE division is ~10 instructions
+// and a slow-path branch; three of them per ray were 2.6 % of all instructions this kernel issues.)
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
 
 __device__ __forceinline__ RayDir make_raydir(float wx, float wy, float wz) {
   const float tiny = 8.67361737988403547e-19f;  // 2^-60: no 0 * inf can arise
@@ -69,9 +88,9 @@ __device__ __forceinline__ RayDir make_raydir(float wx, float wy, float wz) {
   const float dy = fabsf(wy) < tiny ? copysignf(tiny, wy) : wy;
   const float dz = fabsf(wz) < tiny ? copysignf(tiny, wz) : wz;
   RayDir r;
-  r.idx = __fdiv_rn(1.0f, dx);
-  r.idy = __fdiv_rn(1.0f, dy);
-  r.idz = __fdiv_rn(1.0f, dz);
+  r.idx = fast_rcp(dx);
+  r.idy = fast_rcp(dy);
+  r.idz = fast_rcp(dz);
   r.oct = (r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u);
   return r;
 }
@@ -119,8 +138,9 @@ __device__ __forceinline__ uint32_t nibble_prefix(uint32_t counts, uint32_t slot
 // byte i of the 8 quantised planes (w0 = slots 0-3, w1 = slots 4-7) as the float 1 + q * 2^-15:
 // one PRMT drops the byte into bits 8-15 under the exponent of 1.0 — no integer-to-float conversion
 // (I2F runs on the quarter-rate XU pipe; it was the top pipe of the first version of this kernel).
-__device__ __forceinline__ float qplane(uint32_t w0, uint32_t w1, int i) {
-  return __uint_as_float(__byte_perm(i < 4 ? w0 : w1, 0x3F800000u, 0x7604u + ((uint32_t)(i & 3) << 4)));
+// `one` = DevAccel::one.
+__device__ __forceinline__ float qplane(uint32_t w0, uint32_t w1, int i, uint32_t one) {
+  return __uint_as_float(__byte_perm(i < 4 ? w0 : w1, one, 0x7604u + ((uint32_t)(i & 3) << 4)));
 }
 
 // (a & mask) | (b & ~mask) as ONE LOP3 (nvcc narrows the masks of the plain expression and emits two)
@@ -174,12 +194,13 @@ __device__ __forceinline__ NodeHits node_test(const DevAccel& A, uint32_t node, 
   // instructions per child instead of the 6.3 of the clamp / compare / select form (+4 % Mrays/s,
   // profiles/r01_sweep_sign_hits.log).  A NaN (inf - inf) reads as "hit": conservative.
   const float dms = dmax * PHOS_SLAB_SLACK;
+  const uint32_t one = A.one;
   uint32_t miss = 0u;
 #pragma unroll
   for (int i = 7; i >= 0; --i) {
-    const float tnx = __fmaf_rn(qplane(nx0, nx1, i), sx, bx), tfx = __fmaf_rn(qplane(fx0, fx1, i), sx, bx);
-    const float tny = __fmaf_rn(qplane(ny0, ny1, i), sy, by), tfy = __fmaf_rn(qplane(fy0, fy1, i), sy, by);
-    const float tnz = __fmaf_rn(qplane(nz0, nz1, i), sz, bz), tfz = __fmaf_rn(qplane(fz0, fz1, i), sz, bz);
+    const float tnx = __fmaf_rn(qplane(nx0, nx1, i, one), sx, bx), tfx = __fmaf_rn(qplane(fx0, fx1, i, one), sx, bx);
+    const float tny = __fmaf_rn(qplane(ny0, ny1, i, one), sy, by), tfy = __fmaf_rn(qplane(fy0, fy1, i, one), sy, by);
+    const float tnz = __fmaf_rn(qplane(nz0, nz1, i, one), sz, bz), tfz = __fmaf_rn(qplane(fz0, fz1, i, one), sz, bz);
     const float tn = fmaxf(fmaxf(tnx, tny), tnz);
     const float tf = fminf(fminf(tfx, tfy), tfz);
     const float a = __fmaf_rn(tf, PHOS_SLAB_SLACK, -tn);

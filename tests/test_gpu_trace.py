@@ -26,6 +26,19 @@ def test_golden_vectors_bit_exact(device, case):
         assert len(mismatches(rays, got, want)) == 0, (case, batch)
 
 
+def test_deep_tree_instantiation_bit_exact(device, monkeypatch):
+    """The kernel instantiation with the local-memory spill tier (trees deeper than the shared-memory stack; no
+    re-grouped tree needs it) returns the same bits: forced through PHOS_TRACE_DEEP on the golden vectors."""
+    monkeypatch.setenv("PHOS_TRACE_DEEP", "1")
+    z = load_golden(CASES[-1])
+    nodes, packets = z["nodes"], z["packets"]
+    device.upload_accel(nodes, len(nodes) // 288, packets, len(packets) // 384)
+    for batch in BATCHES:
+        rays = golden_rays(z, batch)
+        want = golden_out(z, batch, "linear", rays)
+        assert len(mismatches(rays, device.trace(rays.copy()), want)) == 0, batch
+
+
 def test_device_resident_path_equals_host_pointer_path(device):
     sc = scenes.heightfield(64)
     device.preprocess(sc)
