@@ -132,7 +132,8 @@ int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t s
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * ctx->trace_blocks_per_sm);
   // trees that fit the shared-memory stack (every re-grouped tree so far) run the instantiation without a spill tier
   // (PHOS_TRACE_DEEP=1 forces the deep instantiation: tests/test_gpu_trace.py)
-  const bool deep = ctx->stats.max_depth + 2 > (uint32_t)kSmemStack || std::getenv("PHOS_TRACE_DEEP") != nullptr;
+  // (a ray holds at most one pending sibling group per level below the root: max_depth entries)
+  const bool deep = ctx->stats.max_depth > (uint32_t)kSmemStack || std::getenv("PHOS_TRACE_DEEP") != nullptr;
   if (count) trace_kernel<true, true><<<grid, kTraceBlock, 0, stream>>>(a);
   else if (deep) trace_kernel<false, true><<<grid, kTraceBlock, 0, stream>>>(a);
   else trace_kernel<false, false><<<grid, kTraceBlock, 0, stream>>>(a);

@@ -105,7 +105,7 @@ def main():
                 else:
                     os.environ[k] = v
             print(f"{wl:14s} {os.path.basename(spec):30s} {traced/np.mean(ms)/1e3:9.1f} Mrays/s  min {traced/np.min(ms)/1e3:9.1f}  "
-                  f"rays {traced} nodes/ray {nodes/max(traced,1):.2f} tris/ray {tris/max(traced,1):.2f} hit {out.hit.mean():.3f} same={sig == ref}", flush=True)
+                  f"depth {dev.accel_stats().max_depth} rays {traced} nodes/ray {nodes/max(traced,1):.2f} tris/ray {tris/max(traced,1):.2f} hit {out.hit.mean():.3f} same={sig == ref}", flush=True)
             dr.free()
             dev.close()
 
