@@ -45,7 +45,7 @@ struct phos_ctx {
   unsigned long long* d_counters = nullptr;
   uint64_t launches = 0;
   phos::PipeLane pipe[phos::kPipe];
-  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr, s_in2 = nullptr;
   phos::RenderState* render = nullptr;
   void* d_flush = nullptr;  // L2 flush scratch (bench hygiene)
   int flush_value = 0;

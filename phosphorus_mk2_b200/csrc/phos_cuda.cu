@@ -182,7 +182,7 @@ phos_ctx* phos_cuda_create(int device, const phos_options* options) {
   if (options) ctx->opt = *options;
   else ctx->opt = phos_options{16, 16, 9};
   bool ok = cuda_ok(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  for (cudaStream_t* st : {&ctx->s_in, &ctx->s_cmp, &ctx->s_out})
+  for (cudaStream_t* st : {&ctx->s_in, &ctx->s_cmp, &ctx->s_out, &ctx->s_in2})
     ok = ok && cuda_ok(nullptr, cudaStreamCreateWithFlags(st, cudaStreamNonBlocking), "cudaStreamCreate");
   for (int i = 0; ok && i < kPipe; ++i)
     for (cudaEvent_t* ev : {&ctx->pipe[i].ev_in, &ctx->pipe[i].ev_cmp, &ctx->pipe[i].ev_out})
@@ -211,7 +211,7 @@ void phos_cuda_destroy(phos_ctx* ctx) {
     for (cudaEvent_t ev : {ctx->pipe[i].ev_in, ctx->pipe[i].ev_cmp, ctx->pipe[i].ev_out})
       if (ev) cudaEventDestroy(ev);
   }
-  for (cudaStream_t st : {ctx->s_in, ctx->s_cmp, ctx->s_out})
+  for (cudaStream_t st : {ctx->s_in, ctx->s_cmp, ctx->s_out, ctx->s_in2})
     if (st) cudaStreamDestroy(st);
   phos_render_release(ctx);
   if (ctx->d_nodes) cudaFree(ctx->d_nodes);
@@ -345,6 +345,10 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
   // The write-back runs on a handful of CTAs: its posted writes share the link's outbound queue with the read
   // requests of the up-copies, and a full grid starves them (measured, profiles/r01_e2e_pipeline.log: 4 CTAs
   // 1.84 ms per 2 M-ray frame, a full grid 2.06-2.24 ms; moving d / flags by copy engine instead changes nothing).
+  // consecutive chunks go up on two streams: the next copy is already queued at the copy engine when one ends
+  // (profiles/r01_e2e_pipeline.log: 1.98-2.01 -> 1.84-1.88 ms per 2 M-ray frame at 256 Ki-ray chunks)
+  int in_streams = 2;
+  if (const char* e = std::getenv("PHOS_E2E_IN_STREAMS")) in_streams = std::atoi(e);
   int wb_ctas = 4;
   if (const char* e = std::getenv("PHOS_E2E_WB_CTAS")) wb_ctas = std::max(1, std::atoi(e));
   const char* dbg = std::getenv("PHOS_E2E_DEBUG");  // timing probes only (tools/e2e_probe.py): "noin" / "noout" skip a stage
@@ -353,17 +357,18 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
     const uint64_t cnt = std::min(chunk, n - base);
     PipeLane& L = ctx->pipe[slot];
     const size_t dstride = (size_t)((const char*)L.rays.py - (const char*)L.rays.px);
-    if (L.used) ok = cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_in, L.ev_out, 0), "pipeline wait");  // slot free again
+    cudaStream_t sin = (in_streams > 1 && (slot & 1)) ? ctx->s_in2 : ctx->s_in;  // up-copies of consecutive chunks on two streams
+    if (L.used) ok = cuda_ok(ctx, cudaStreamWaitEvent(sin, L.ev_out, 0), "pipeline wait");  // slot free again
     if (ok && pitched && !dbg_noin)
       ok = cuda_ok(ctx, cudaMemcpy2DAsync(L.rays.px, dstride, slab[0] + base * 4, (size_t)hstride, cnt * 4, sparse ? 8 : 12,
-                                          cudaMemcpyHostToDevice, ctx->s_in),
+                                          cudaMemcpyHostToDevice, sin),
                    "H2D rays");
-    if (ok && sparse) ok = cuda_ok(ctx, cudaMemsetAsync(L.rays.mesh, 0xff, cnt * 4, ctx->s_in), "memset(mesh)");
+    if (ok && sparse) ok = cuda_ok(ctx, cudaMemsetAsync(L.rays.mesh, 0xff, cnt * 4, sin), "memset(mesh)");
     for (int k = 0; ok && !pitched && k < 12; ++k) {
       const char* src = (const char*)in_ptr(*rays, k) + base * 4;
-      ok = cuda_ok(ctx, cudaMemcpyAsync((void*)in_ptr(L.rays, k), src, cnt * 4, cudaMemcpyHostToDevice, ctx->s_in), "H2D rays");
+      ok = cuda_ok(ctx, cudaMemcpyAsync((void*)in_ptr(L.rays, k), src, cnt * 4, cudaMemcpyHostToDevice, sin), "H2D rays");
     }
-    ok = ok && cuda_ok(ctx, cudaEventRecord(L.ev_in, ctx->s_in), "pipeline record") &&
+    ok = ok && cuda_ok(ctx, cudaEventRecord(L.ev_in, sin), "pipeline record") &&
          cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_cmp, L.ev_in, 0), "pipeline wait");
     if (!ok) break;
     const int rc = launch_trace(ctx, L.rays, cnt, ctx->s_cmp, ctx->d_counters + 16 + slot, false);
@@ -394,6 +399,7 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
   }
   if (!ok) {
     cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->s_in2);
     cudaStreamSynchronize(ctx->s_cmp);
     cudaStreamSynchronize(ctx->s_out);
     return PHOS_ERR_CUDA;

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -88,13 +89,16 @@ __global__ void paths_init_kernel(const FrameArgs A, phos_rays rays, uint32_t* _
   A.depth[q] = 0u;
 }
 
+#ifndef PHOS_GS_BLOCKS
+#define PHOS_GS_BLOCKS 16
+#endif
+constexpr uint32_t kGridStrideBlocksPerSm = PHOS_GS_BLOCKS;  // grid cap of the grid-stride kernels (blocks of 256 per SM)
+
 // Interaction + next-event shadow ray for every live slot: build_interactions
 // (deferred_shading_kernel.hpp:39-72), fresh_light_samples (sampling.cpp:160-180), area_light_t::sample
 // (light.cpp:47-71), light_sampler_t (spt.hpp:116-148).
-__global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const uint32_t* __restrict__ slot_path, int cur,
-                                 phos_rays sh) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= A.count[cur]) return;
+__device__ __forceinline__ void shade_nee_slot(const FrameArgs& A, const phos_rays& rays, const uint32_t* __restrict__ slot_path,
+                                               const phos_rays& sh, uint32_t i) {
   const uint32_t flags = rays.flags[i];
   if (!(flags & PHOS_HIT) || A.scene.nlights == 0u) {  // a missed slot gets a masked query (spt.hpp:139-143)
     sh.flags[i] = PHOS_SHADOW | PHOS_MASKED;
@@ -147,6 +151,17 @@ __global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const 
   sh.flags[i] = ish ? PHOS_SHADOW : (PHOS_SHADOW | PHOS_MASKED);
 }
 
+// Grid-stride over the live slots (the queue length lives in HBM) on a grid capped at kGridStrideBlocksPerSm blocks
+// per SM: with the 16-64 M-slot wavefronts of a frame, one block per 256 slots meant up to 260 k blocks per launch,
+// most of which start, read the count and leave (profiles/r01_render_wavefront_size.log: Cornell 31.7 -> 15.7 ms per
+// frame at 16.7 M slots, config 4 206 -> 198 ms at 64 Mi).
+__global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const uint32_t* __restrict__ slot_path, int cur,
+                                 phos_rays sh) {
+  const uint32_t count = A.count[cur];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    shade_nee_slot(A, rays, slot_path, sh, i);
+}
+
 // integrator_t::operator() (spt.hpp:161-210) with li (:212-255), sample_bsdf (:257-305) and
 // terminate_path (:307-328); survivors are appended to the next ray stream.
 #ifndef PHOS_INTEGRATE_MIN_BLOCKS
@@ -154,8 +169,10 @@ __global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const 
 #endif
 __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kernel(const FrameArgs A, const phos_rays rays, const phos_rays sh,
                                  const uint32_t* __restrict__ slot_path, int cur, phos_rays next, uint32_t* __restrict__ next_path) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < A.count[cur];
+ // grid-stride over the live slots, a whole warp at a time (the compaction below is a warp collective)
+ const uint32_t count = A.count[cur];
+ for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < count; i += gridDim.x * blockDim.x) {
+  const bool valid = i < count;
   bool alive = false;
   uint32_t q = 0, nflags = 0;
   v3 no = V(0, 0, 0), nw = V(0, 0, 0);
@@ -233,7 +250,7 @@ __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kern
   }
   // compaction: one atomic per warp reserves slots for all its survivors
   const unsigned live = __ballot_sync(0xffffffffu, alive);
-  if (live == 0u) return;
+  if (live == 0u) continue;
   const unsigned lane = threadIdx.x & 31u;
   uint32_t base = 0;
   if (lane == (unsigned)(__ffs(live) - 1)) base = atomicAdd(&A.count[cur ^ 1], (uint32_t)__popc(live));
@@ -250,6 +267,7 @@ __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kern
     next.flags[slot] = (nflags & BSDF_SPECULAR_F) ? PHOS_SPECULAR : 0u;  // rays->specular_bounce (spt.hpp:302)
     next_path[slot] = q;
   }
+ }
 }
 
 // channels.primary->add(x, y, r * (1 / (spp * pps))) per sample (cpu.cpp:175-198), samples in order
@@ -340,8 +358,22 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   if (total == 0) return PHOS_OK;
   if (total > 0x7fffffffull) return fail(ctx, PHOS_ERR_INVALID, "too many pixels in one render call");
   const uint32_t P = (uint32_t)total;
-  // samples in flight: enough paths to fill the machine, bounded by the wavefront's memory
-  const uint64_t target = 4ull << 20;
+  // Paths in flight per batch.  Every trace launch ends in a tail in which the last long rays finish on a draining
+  // machine (a ray lives ~50 us; the slowest of a launch several times that), and a batch has 2 x depth of them: at
+  // 4 Mi paths the tails were a quarter of a config-4 frame (profiles/r01_render_wavefront_size.log: 4 / 8 / 16 / 32 /
+  // 64 Mi paths = 513 / 582 / 628 / 656 / 670 M samples/s).  64 Mi paths are 13 GB of wavefront state (196 B per path)
+  // on a 180 GB device; never more than a quarter of what is free.  PHOS_WAVEFRONT_PATHS overrides.
+  uint64_t target = 64ull << 20;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const uint64_t afford = ((uint64_t)free_b + R.wf.capacity * 196ull) / 4ull / 196ull;
+      target = std::min<uint64_t>(target, std::max<uint64_t>(afford, 1ull << 20));
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (const char* e = std::getenv("PHOS_WAVEFRONT_PATHS")) target = std::max<uint64_t>(1ull << 16, std::strtoull(e, nullptr, 10));
   uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(spp_end - spp_begin, target / P));
   if (!R.ensure_wavefront(ctx, (uint64_t)P * batch, P)) return PHOS_ERR_CUDA;
   if (!R.set_tiles(ctx, tiles, offsets.data(), n_tiles)) return PHOS_ERR_CUDA;
@@ -391,6 +423,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
     A.Q = P * ns;
     A.spp_begin = s0;
     const uint32_t blocks = (A.Q + 255) / 256;
+    const uint32_t gs_blocks = std::min<uint32_t>(blocks, (uint32_t)ctx->sm_count * kGridStrideBlocksPerSm);  // grid-stride kernels
     paths_init_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.slot_path[0]);
     ctx->launches++;
     for (uint32_t b = 0; b < A.max_depth; ++b) {
@@ -399,7 +432,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
       ctx->launches++;
       int rc = launch_trace(ctx, W.rays[cur], A.Q, st, ctx->d_counters + 24, false, W.count + cur);
       if (rc) return rc;
-      shade_nee_kernel<<<blocks, 256, 0, st>>>(A, W.rays[cur], W.slot_path[cur], cur, W.shadow);
+      shade_nee_kernel<<<gs_blocks, 256, 0, st>>>(A, W.rays[cur], W.slot_path[cur], cur, W.shadow);
       ctx->launches++;
       if (b == 0 && R.film_normals) {
         normals_channel_kernel<<<(P + 255) / 256, 256, 0, st>>>(A, W.rays[0], ns, R.film_normals);
@@ -407,7 +440,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
       }
       rc = launch_trace(ctx, W.shadow, A.Q, st, ctx->d_counters + 25, false, W.count + cur);
       if (rc) return rc;
-      integrate_kernel<<<blocks, 256, 0, st>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1]);
+      integrate_kernel<<<gs_blocks, 256, 0, st>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1]);
       ctx->launches++;
     }
     film_accumulate_kernel<<<(P + 255) / 256, 256, 0, st>>>(A, R.film);
@@ -475,16 +508,17 @@ int phos_cuda_wavefront_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_t
   A.light_pdf = W.light_pdf;
   A.count = W.count;
   const uint32_t blocks = (P + 255) / 256;
+  const uint32_t gs_blocks = std::min<uint32_t>(blocks, (uint32_t)ctx->sm_count * kGridStrideBlocksPerSm);
   paths_init_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.slot_path[0]);
   int rc = launch_trace(ctx, W.rays[0], P, st, ctx->d_counters + 24, false, W.count);
   if (rc) return rc;
-  shade_nee_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.slot_path[0], 0, W.shadow);
+  shade_nee_kernel<<<gs_blocks, 256, 0, st>>>(A, W.rays[0], W.slot_path[0], 0, W.shadow);
   const phos_rays* src = &W.shadow;
   uint32_t n = P;
   if (which == 0) {
     rc = launch_trace(ctx, W.shadow, P, st, ctx->d_counters + 25, false, W.count);
     if (rc) return rc;
-    integrate_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.shadow, W.slot_path[0], 0, W.rays[1], W.slot_path[1]);
+    integrate_kernel<<<gs_blocks, 256, 0, st>>>(A, W.rays[0], W.shadow, W.slot_path[0], 0, W.rays[1], W.slot_path[1]);
     if (!cuda_ok(ctx, cudaMemcpyAsync(&n, W.count + 1, 4, cudaMemcpyDeviceToHost, st), "read queue length") ||
         !cuda_ok(ctx, cudaStreamSynchronize(st), "wavefront_rays"))
       return PHOS_ERR_CUDA;

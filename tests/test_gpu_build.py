@@ -61,7 +61,9 @@ def test_device_build_at_full_size_and_frame_parity(device, oracle):
     device.build_accel(sc)
     st = device.accel_stats()
     assert st.triangles == 1048576 and st.max_depth + 2 <= 92
-    assert st.repack_seconds < 0.5  # the device build itself: milliseconds (the host build + re-pack takes ~1 s)
+    # the device build itself takes milliseconds (3-30 ms; printed below).  No tight bound here: once in a while the
+    # cudaMallocs inside it stall for a second on a fresh box (seen: 1.26 s), and this is a parity test, not a benchmark
+    assert st.repack_seconds < 30.0
     device.camera_rays(tiles, dr)
     device.trace_device(dr)
     gpu_nodes, gpu_tris = device.trace_count(dr)
