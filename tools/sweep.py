@@ -20,14 +20,16 @@ def main():
     ap.add_argument("--workloads", default="spheres,terrain_inc")
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--terrain-n", type=int, default=2237)
+    ap.add_argument("--film", default="1920x1080", help="film size WxH (rays per launch of the camera workloads)")
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
+    fw, fh = (int(v) for v in a.film.split("x"))
     for wl in a.workloads.split(","):
         t0 = time.time()
         if wl == "spheres":
-            sc = scenes.sphere_field()
+            sc = scenes.sphere_field(width=fw, height=fh)
         else:
-            sc = scenes.terrain(n=a.terrain_n)
+            sc = scenes.terrain(n=a.terrain_n, width=fw, height=fh)
         acc = Accel(sc)
         host = None
         wave = None
