@@ -286,13 +286,22 @@ int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
   return PHOS_OK;
 }
 
-bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixels) {
-  if (wf.capacity >= paths && wf.pixel) {
-    // the pixel table is sized by the largest batch seen; regrow below if this one has more pixels
-  }
+static void release_one(Wavefront& wf) {
+  free_rays(wf.rays[0]);
+  free_rays(wf.rays[1]);
+  free_rays(wf.shadow);
+  void* ptrs[] = {wf.slot_path[0], wf.slot_path[1], wf.count, wf.n, wf.light_pdf, wf.beta, wf.rad, wf.depth, wf.pixel};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  wf = Wavefront();
+}
+
+bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixels, int which) {
+  Wavefront& wf = which ? this->wf2 : this->wf;
   if (wf.capacity < paths || wf.pixel_capacity < pixels) {
     cudaStreamSynchronize(ctx->stream);
-    release_wavefront();
+    cudaStreamSynchronize(ctx->s_cmp);
+    release_one(wf);
     const uint64_t cap = std::max<uint64_t>(paths, 1024);
     bool ok = alloc_rays(ctx, cap, wf.rays[0]) && alloc_rays(ctx, cap, wf.rays[1]) && alloc_rays(ctx, cap, wf.shadow);
     auto get = [&](void** p, size_t bytes) { return ok && (ok = cuda_ok(ctx, cudaMalloc(p, bytes), "cudaMalloc(wavefront)")); };
@@ -306,7 +315,7 @@ bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixel
     get((void**)&wf.depth, cap * 4);
     get((void**)&wf.pixel, std::max<uint64_t>(pixels, 1024) * 4);
     if (!ok) {
-      release_wavefront();
+      release_one(wf);
       return false;
     }
     wf.capacity = cap;
@@ -316,13 +325,8 @@ bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixel
 }
 
 void RenderState::release_wavefront() {
-  free_rays(wf.rays[0]);
-  free_rays(wf.rays[1]);
-  free_rays(wf.shadow);
-  void* ptrs[] = {wf.slot_path[0], wf.slot_path[1], wf.count, wf.n, wf.light_pdf, wf.beta, wf.rad, wf.depth, wf.pixel};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
-  wf = Wavefront();
+  release_one(wf);
+  release_one(wf2);
 }
 
 bool RenderState::set_tiles(phos_ctx* ctx, const phos_tile* tiles, const unsigned long long* offsets, uint32_t n) {

@@ -45,11 +45,12 @@ struct RenderState {
   float* film_normals = nullptr;  // W * H * 3, the NORMALS channel (allocated by phos_cuda_enable_normals)
   float* d_jitter = nullptr;
   uint32_t jitter_capacity = 0;
-  Wavefront wf;
+  Wavefront wf;   // the wavefront of a frame (and of phos_cuda_wavefront_rays)
+  Wavefront wf2;  // second wavefront: batches of a frame alternate between two streams (wavefront.cu)
 
   int upload(phos_ctx* ctx, const phos_scene_desc* scene);
   bool set_tiles(phos_ctx* ctx, const phos_tile* tiles, const unsigned long long* offsets, uint32_t n);
-  bool ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixels);
+  bool ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixels, int which = 0);
   void release_wavefront();
   void release();
 };

@@ -361,29 +361,43 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   // Paths in flight per batch.  Every trace launch ends in a tail in which the last long rays finish on a draining
   // machine (a ray lives ~50 us; the slowest of a launch several times that), and a batch has 2 x depth of them: at
   // 4 Mi paths the tails were a quarter of a config-4 frame (profiles/r01_render_wavefront_size.log: 4 / 8 / 16 / 32 /
-  // 64 Mi paths = 513 / 582 / 628 / 656 / 670 M samples/s).  64 Mi paths are 13 GB of wavefront state (196 B per path)
-  // on a 180 GB device; never more than a quarter of what is free.  PHOS_WAVEFRONT_PATHS overrides.
+  // 64 Mi paths = 513 / 582 / 628 / 656 / 670 M samples/s).  64 Mi paths (over both wavefronts) are 13 GB of wavefront
+  // state (196 B per path) on a 180 GB device; never more than a quarter of what is free.  PHOS_WAVEFRONT_PATHS overrides.
   uint64_t target = 64ull << 20;
   {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      const uint64_t afford = ((uint64_t)free_b + R.wf.capacity * 196ull) / 4ull / 196ull;
+      const uint64_t afford = ((uint64_t)free_b + (R.wf.capacity + R.wf2.capacity) * 196ull) / 4ull / 196ull;
       target = std::min<uint64_t>(target, std::max<uint64_t>(afford, 1ull << 20));
     } else {
       cudaGetLastError();
     }
   }
   if (const char* e = std::getenv("PHOS_WAVEFRONT_PATHS")) target = std::max<uint64_t>(1ull << 16, std::strtoull(e, nullptr, 10));
-  uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(spp_end - spp_begin, target / P));
-  if (!R.ensure_wavefront(ctx, (uint64_t)P * batch, P)) return PHOS_ERR_CUDA;
+  // Two wavefronts (PHOS_WAVEFRONTS=2, off by default): the batches of a frame alternate between two streams, so the
+  // tail of one batch's launches (a launch cannot end before its longest ray does) runs under the other batch's full
+  // launches.  Film accumulation stays in sample order (an event chains the two streams there), so the image does not
+  // depend on it.  Measured on one GPU (profiles/r01_render_wavefront_size.log): config 4 215.6 -> 211.9 ms per frame,
+  // but the Cornell box 15.8 -> 19.7 ms (short rays, no tails to hide; the two wavefronts only contend) — hence off;
+  // the case it is meant for is the tile-partitioned frame on 8 GPUs, where each rank is left with a single batch.
+  // Always one wavefront when the NORMALS channel is on (its "last sample that hit" is order dependent).
+  int nw = 1;
+  if (const char* e = std::getenv("PHOS_WAVEFRONTS")) nw = std::atoi(e) >= 2 ? 2 : 1;
+  if (R.film_normals || spp_end - spp_begin < 2) nw = 1;
+  uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(spp_end - spp_begin, target / ((uint64_t)P * nw)));
+  if (nw == 2) batch = std::min<uint32_t>(batch, (spp_end - spp_begin + 1) / 2);  // at least two batches to overlap
+  for (int w = 0; w < nw; ++w)
+    if (!R.ensure_wavefront(ctx, (uint64_t)P * batch, P, w)) return PHOS_ERR_CUDA;
   if (!R.set_tiles(ctx, tiles, offsets.data(), n_tiles)) return PHOS_ERR_CUDA;
-  Wavefront& W = R.wf;
+  Wavefront* WF[2] = {&R.wf, &R.wf2};
   cudaStream_t st = ctx->stream;
+  cudaStream_t streams[2] = {ctx->stream, ctx->s_cmp};
 
+  for (int w = 0; w < nw; ++w)
   for (uint32_t first = 0; first < n_tiles; first += 65535) {
     const uint32_t cnt = std::min<uint32_t>(65535, n_tiles - first);
     pixel_table_kernel<<<dim3((max_px + 255) / 256, cnt), 256, 0, st>>>(R.d_tiles + first, R.d_tile_offsets + first, R.camera.width,
-                                                                         W.pixel);
+                                                                         WF[w]->pixel);
     ctx->launches++;
   }
   // film jitter table for this (seed, spp_total)
@@ -402,51 +416,85 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
     cudaStreamSynchronize(st);  // jit goes out of scope
   }
 
-  FrameArgs A;
-  A.cam = R.camera;
-  A.scene = R.scene;
-  A.P = P;
-  A.seed = seed;
-  A.max_depth = ctx->opt.path_depth;
-  A.scale = 1.0f / (float)(spp_total * ctx->opt.paths_per_sample);
-  A.jitter = R.d_jitter;
-  A.pixel = W.pixel;
-  A.beta = W.beta;
-  A.rad = W.rad;
-  A.depth = W.depth;
-  A.n = W.n;
-  A.light_pdf = W.light_pdf;
-  A.count = W.count;
-
-  for (uint32_t s0 = spp_begin; s0 < spp_end; s0 += batch) {
+  FrameArgs AW[2];
+  for (int w = 0; w < nw; ++w) {
+    FrameArgs& A = AW[w];
+    const Wavefront& W = *WF[w];
+    A.cam = R.camera;
+    A.scene = R.scene;
+    A.P = P;
+    A.seed = seed;
+    A.max_depth = ctx->opt.path_depth;
+    A.scale = 1.0f / (float)(spp_total * ctx->opt.paths_per_sample);
+    A.jitter = R.d_jitter;
+    A.pixel = W.pixel;
+    A.beta = W.beta;
+    A.rad = W.rad;
+    A.depth = W.depth;
+    A.n = W.n;
+    A.light_pdf = W.light_pdf;
+    A.count = W.count;
+  }
+  // the second stream starts after the set-up on the first (pixel tables, jitter table); film_accumulate launches are
+  // chained in batch order; the first stream ends by waiting for the second
+  cudaEvent_t ev_setup = nullptr, ev_film[2] = {nullptr, nullptr};
+  bool ok = true;
+  if (nw == 2) {
+    ok = cuda_ok(ctx, cudaEventCreateWithFlags(&ev_setup, cudaEventDisableTiming), "event") &&
+         cuda_ok(ctx, cudaEventCreateWithFlags(&ev_film[0], cudaEventDisableTiming), "event") &&
+         cuda_ok(ctx, cudaEventCreateWithFlags(&ev_film[1], cudaEventDisableTiming), "event") &&
+         cuda_ok(ctx, cudaEventRecord(ev_setup, st), "event record") &&
+         cuda_ok(ctx, cudaStreamWaitEvent(streams[1], ev_setup, 0), "event wait");
+  }
+  int rc = PHOS_OK;
+  uint32_t k = 0;
+  for (uint32_t s0 = spp_begin; ok && rc == PHOS_OK && s0 < spp_end; s0 += batch, ++k) {
+    const int w = nw == 2 ? (int)(k & 1u) : 0;
+    cudaStream_t sk = streams[w];
+    FrameArgs& A = AW[w];
+    Wavefront& W = *WF[w];
+    unsigned long long* cursors = ctx->d_counters + 24 + 2 * w;
     const uint32_t ns = std::min(batch, spp_end - s0);
     A.Q = P * ns;
     A.spp_begin = s0;
     const uint32_t blocks = (A.Q + 255) / 256;
     const uint32_t gs_blocks = std::min<uint32_t>(blocks, (uint32_t)ctx->sm_count * kGridStrideBlocksPerSm);  // grid-stride kernels
-    paths_init_kernel<<<blocks, 256, 0, st>>>(A, W.rays[0], W.slot_path[0]);
+    paths_init_kernel<<<blocks, 256, 0, sk>>>(A, W.rays[0], W.slot_path[0]);
     ctx->launches++;
-    for (uint32_t b = 0; b < A.max_depth; ++b) {
+    for (uint32_t b = 0; b < A.max_depth && rc == PHOS_OK; ++b) {
       const int cur = (int)(b & 1u);
-      zero_u32_kernel<<<1, 1, 0, st>>>(W.count + (cur ^ 1));
+      zero_u32_kernel<<<1, 1, 0, sk>>>(W.count + (cur ^ 1));
       ctx->launches++;
-      int rc = launch_trace(ctx, W.rays[cur], A.Q, st, ctx->d_counters + 24, false, W.count + cur);
-      if (rc) return rc;
-      shade_nee_kernel<<<gs_blocks, 256, 0, st>>>(A, W.rays[cur], W.slot_path[cur], cur, W.shadow);
+      rc = launch_trace(ctx, W.rays[cur], A.Q, sk, cursors, false, W.count + cur);
+      if (rc) break;
+      shade_nee_kernel<<<gs_blocks, 256, 0, sk>>>(A, W.rays[cur], W.slot_path[cur], cur, W.shadow);
       ctx->launches++;
       if (b == 0 && R.film_normals) {
-        normals_channel_kernel<<<(P + 255) / 256, 256, 0, st>>>(A, W.rays[0], ns, R.film_normals);
+        normals_channel_kernel<<<(P + 255) / 256, 256, 0, sk>>>(A, W.rays[0], ns, R.film_normals);
         ctx->launches++;
       }
-      rc = launch_trace(ctx, W.shadow, A.Q, st, ctx->d_counters + 25, false, W.count + cur);
-      if (rc) return rc;
-      integrate_kernel<<<gs_blocks, 256, 0, st>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1]);
+      rc = launch_trace(ctx, W.shadow, A.Q, sk, cursors + 1, false, W.count + cur);
+      if (rc) break;
+      integrate_kernel<<<gs_blocks, 256, 0, sk>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1]);
       ctx->launches++;
     }
-    film_accumulate_kernel<<<(P + 255) / 256, 256, 0, st>>>(A, R.film);
+    if (rc) break;
+    if (nw == 2 && k > 0) ok = cuda_ok(ctx, cudaStreamWaitEvent(sk, ev_film[(k - 1) & 1u], 0), "event wait");  // sample order
+    film_accumulate_kernel<<<(P + 255) / 256, 256, 0, sk>>>(A, R.film);
     ctx->launches++;
+    if (nw == 2) ok = ok && cuda_ok(ctx, cudaEventRecord(ev_film[k & 1u], sk), "event record");
   }
-  return cuda_ok(ctx, cudaGetLastError(), "render launch") ? PHOS_OK : PHOS_ERR_CUDA;
+  if (nw == 2) {
+    // everything the second stream did is ordered before whatever the caller enqueues next on the first
+    if (ok && rc == PHOS_OK && k > 0)
+      ok = cuda_ok(ctx, cudaEventRecord(ev_setup, streams[1]), "event record") && cuda_ok(ctx, cudaStreamWaitEvent(st, ev_setup, 0), "event wait");
+    else
+      cudaStreamSynchronize(streams[1]);
+    for (cudaEvent_t e : {ev_setup, ev_film[0], ev_film[1]})
+      if (e) cudaEventDestroy(e);
+  }
+  if (rc) return rc;
+  return ok && cuda_ok(ctx, cudaGetLastError(), "render launch") ? PHOS_OK : PHOS_ERR_CUDA;
 }
 
 // The ray streams of BASELINE config 3, produced by the pipeline itself: run ONE bounce of sample
