@@ -152,9 +152,10 @@ __device__ __forceinline__ void shade_nee_slot(const FrameArgs& A, const phos_ra
 }
 
 // Grid-stride over the live slots (the queue length lives in HBM) on a grid capped at kGridStrideBlocksPerSm blocks
-// per SM: with the 16-64 M-slot wavefronts of a frame, one block per 256 slots meant up to 260 k blocks per launch,
-// most of which start, read the count and leave (profiles/r01_render_wavefront_size.log: Cornell 31.7 -> 15.7 ms per
-// frame at 16.7 M slots, config 4 206 -> 198 ms at 64 Mi).
+// per SM: with the 16-64 M-slot wavefronts of a frame, one block per 256 slots would be up to 260 k blocks per launch,
+// most of which start, read the count and leave in the late bounces.  Measured equal within the box-to-box noise at
+// 64 Mi paths (config 4: 198-216 ms per frame against 206 ms) and 3 % slower at 4 Mi paths
+// (profiles/r01_render_wavefront_size.log, r01_render_variants.log).
 __global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const uint32_t* __restrict__ slot_path, int cur,
                                  phos_rays sh) {
   const uint32_t count = A.count[cur];
