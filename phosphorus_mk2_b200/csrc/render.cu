@@ -163,6 +163,7 @@ float tri_area(const float* a, const float* b, const float* c) {  // triangle_t:
 // sampling, the closure table, the area lights (one per emissive face set, in mesh -> set order:
 // src/mesh.cpp:108-116, src/scene.cpp:49-55) with their total areas (src/light.cpp:30-45).
 int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
+  paths_cap = 0;  // free memory changes with the scene: ask again at the next render
   const uint32_t nm = d->num_meshes;
   if (nm == 0 || !d->vert_offset || !d->vertices || !d->face_offset || !d->faces || !d->mesh_smooth || !d->set_offset ||
       !d->set_material || !d->set_face_offset || !d->set_faces || (d->num_materials && !d->materials))

@@ -45,6 +45,7 @@ struct RenderState {
   float* film_normals = nullptr;  // W * H * 3, the NORMALS channel (allocated by phos_cuda_enable_normals)
   float* d_jitter = nullptr;
   uint32_t jitter_capacity = 0;
+  uint64_t paths_cap = 0;  // most paths in flight the device memory affords (asked once per scene upload; 0 = not yet)
   Wavefront wf;   // the wavefront of a frame (and of phos_cuda_wavefront_rays)
   Wavefront wf2;  // second wavefront: batches of a frame alternate between two streams (wavefront.cu)
 

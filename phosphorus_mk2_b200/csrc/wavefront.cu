@@ -365,15 +365,15 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   // 64 Mi paths = 513 / 582 / 628 / 656 / 670 M samples/s).  64 Mi paths (over both wavefronts) are 13 GB of wavefront
   // state (196 B per path) on a 180 GB device; never more than a quarter of what is free.  PHOS_WAVEFRONT_PATHS overrides.
   uint64_t target = 64ull << 20;
-  {
+  if (R.paths_cap == 0) {  // asked once per scene upload: cudaMemGetInfo is a driver round trip, not something for every frame
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      const uint64_t afford = ((uint64_t)free_b + (R.wf.capacity + R.wf2.capacity) * 196ull) / 4ull / 196ull;
-      target = std::min<uint64_t>(target, std::max<uint64_t>(afford, 1ull << 20));
-    } else {
+    R.paths_cap = ~0ull;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+      R.paths_cap = std::max<uint64_t>(((uint64_t)free_b + (R.wf.capacity + R.wf2.capacity) * 196ull) / 4ull / 196ull, 1ull << 20);
+    else
       cudaGetLastError();
-    }
   }
+  target = std::min<uint64_t>(target, R.paths_cap);
   if (const char* e = std::getenv("PHOS_WAVEFRONT_PATHS")) target = std::max<uint64_t>(1ull << 16, std::strtoull(e, nullptr, 10));
   // Two wavefronts (PHOS_WAVEFRONTS=2, off by default): the batches of a frame alternate between two streams, so the
   // tail of one batch's launches (a launch cannot end before its longest ray does) runs under the other batch's full

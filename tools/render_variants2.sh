@@ -1,2 +1,3 @@
 run() { python bench.py --render --workload $1 --spp 64 --depth 8 --steps 4 --warmup 2 2>/dev/null | tail -1 | python -c "import sys,json; j=json.loads(sys.stdin.read()); print('$1 $2', round(j['ms_per_step'],2), 'ms', round(j['value']/1e6,1), 'Msamples/s', j['image_mean'])"; }
-for v in "" _imb3 _imb5 _gs8 _gs32 ""; do export PHOS_CUDA_LIB=$PWD/phosphorus_mk2_b200/lib/libphos_cuda$v.so; run cornell "lib$v"; run terrain_ggx "lib$v"; done
+run cornell first; run cornell second; run cornell third; run terrain_ggx x; run cornell fourth
+python -m pytest tests/test_gpu_render.py -m gpu -x -q 2>&1 | tail -2
