@@ -180,6 +180,24 @@ def test_tile_and_sample_partitioning_do_not_change_the_image():
     assert np.array_equal(whole, by_tiles)
 
 
+def test_batching_and_second_wavefront_do_not_change_the_image(monkeypatch):
+    """The frame is cut into batches of PHOS_WAVEFRONT_PATHS paths, optionally alternating between two wavefronts on two
+    streams (PHOS_WAVEFRONTS=2, film accumulation chained in sample order): same film, bit for bit."""
+    sc = scenes.cornell_box(96, 64)
+    acc = Accel(sc)
+    monkeypatch.setenv("PHOS_WAVEFRONTS", "1")
+    whole, n_whole = render_gpu(sc, acc, 16, 5, 3)
+    monkeypatch.setenv("PHOS_WAVEFRONT_PATHS", "65536")  # the smallest allowed: 10 samples per batch here, then a short one
+    batched, n_batched = render_gpu(sc, acc, 16, 5, 3)
+    assert np.array_equal(whole, batched) and n_batched > n_whole
+    monkeypatch.setenv("PHOS_WAVEFRONTS", "2")
+    two, _ = render_gpu(sc, acc, 16, 5, 3)
+    assert np.array_equal(whole, two)
+    monkeypatch.delenv("PHOS_WAVEFRONT_PATHS")
+    two_big, _ = render_gpu(sc, acc, 16, 5, 3)  # one batch per wavefront
+    assert np.array_equal(whole, two_big)
+
+
 def test_render_call_order_errors():
     from phosphorus_mk2_b200.lib import PhosError
     dev = CudaDevice.make(Options(), 0)
