@@ -9,9 +9,9 @@
 //     work, then all of them write their hit records and take the next rays of the warp's chunk
 //     (ballot + popc ranks, no atomics), so a long ray never holds 31 finished lanes hostage;
 //   * warp-voted phases: two ballots per iteration say what every lane wants next; the warp then runs
-//     either one node step (8 quantised child boxes, ~245 instructions) for the lanes that need one,
+//     either one node step (8 quantised child boxes, 240 instructions) for the lanes that need one,
 //     or one triangle step (up to two Möller–Trumbore tests of the open leaf piece, both 48-byte
-//     fetches in flight together, ~150 instructions) for the lanes with pending leaf triangles — the
+//     fetches in flight together, ~175 instructions) for the lanes with pending leaf triangles — the
 //     vote is weighted towards the cheaper triangle step — so both inner loops run converged instead
 //     of every lane dragging the warp through its own leaf loop;
 //   * hit record = the index of the triangle held so far; its ids (and, on an exact tie in t only, its
@@ -20,8 +20,10 @@
 //     stack pointer in a register); a second instantiation (kDeep) with a local-memory spill tier serves
 //     trees deeper than that (the re-grouped trees are 8-10 levels deep and never need it).
 // Measured alternatives that did not pay off (profiles/r01_summary.md): L1 prefetch of the next node,
-// 64 registers / 8 CTAs per SM, sorting the ray stream, fused leaves, other vote biases / refill
-// thresholds, packed FFMA2 plane evaluation.
+// 64 registers / 8 CTAs per SM, 80 registers / 6 CTAs, sorting the ray stream, fused leaves, other vote biases /
+// refill thresholds, 64-ray chunks, shorter claims near the end of the stream, packed FFMA2 plane evaluation,
+// plane bytes decoded on the XU / FMA pipes, smaller shared-memory stacks, the stack base pinned in a register,
+// a per-group distance bound (costed on the host emulation, not built).
 #pragma once
 #include "trace_ray.cuh"
 
