@@ -115,12 +115,19 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   uint32_t cur_cnt = 0, taken = 0, nxt_cnt = 0;
   bool nxt_tma = false, exhausted = false;
 
+  const unsigned long long n_warps = (unsigned long long)gridDim.x * kTraceWarps;
+  bool first_claim = true;
   auto claim = [&](int buf) {  // claim the next chunk of the stream and start staging it into `buf`
     nxt_cnt = 0;
     if (exhausted) return;
     unsigned long long c = 0;
-    if (lane == 0) c = atomicAdd(P.cursor, 1ull);
-    c = __shfl_sync(0xffffffffu, c, 0);
+    if (first_claim) {  // chunk = global warp index: 4144 warps do not queue up on one atomic at the start
+      c = (unsigned long long)blockIdx.x * kTraceWarps + warp;
+      first_claim = false;
+    } else {
+      if (lane == 0) c = atomicAdd(P.cursor, 1ull);
+      c = __shfl_sync(0xffffffffu, c, 0) + n_warps;
+    }
     const unsigned long long base = c * kChunk;
     if (base >= N) {
       exhausted = true;
@@ -194,7 +201,8 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
     const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
     const unsigned nl = __ballot_sync(0xffffffffu, node_work);
     // 2. enough lanes without work (finished rays or empty lanes): retire and refill from the chunk
-    if (__popc(~(tl | nl)) >= kRefillMin) {
+    const int n_tri = __popc(tl), n_node = __popc(nl);  // disjoint sets: the rest of the warp is without work
+    if (32 - n_tri - n_node >= kRefillMin) {
       if (has_ray && !tri_work && !node_work) {
         if (r.tri != kNoTri) {  // something was accepted (accept_hit marks shadow rays too)
           P.rays.d[ridx] = r.d;
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
     }
     // 3. vote: node step or triangle step
     // a triangle step is cheaper than a node step: PHOS_TRI_BIAS weights the vote
-    if (PHOS_TRI_BIAS * __popc(tl) >= __popc(nl)) {
+    if (PHOS_TRI_BIAS * n_tri >= n_node) {
       if (tri_work) {
         if ((lt >> 8) == 0u) {  // open the next hit leaf, nearest octant first
           const uint32_t slot = (__ffs(lt) - 1) ^ rd.oct;
