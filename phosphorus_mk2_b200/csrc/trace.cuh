@@ -1,7 +1,8 @@
 // trace.cuh — the ray-query kernel (sm_100a): persistent warps that drain a ray stream through the
 // node / triangle steps of trace_ray.cuh.
 //
-//   * work distribution: every warp claims 32-ray chunks of the stream from one global cursor; the
+//   * work distribution: every warp starts on the chunk with its own global index and then claims 32-ray chunks
+//     of the rest of the stream from one global cursor (no queue on the atomic when a launch starts); the
 //     chunk's eight input arrays (p, wi, d, flags) are staged into shared memory with TMA bulk copies
 //     (cp.async.bulk + mbarrier), double-buffered so the next chunk lands while the current one is
 //     being traversed; a partial tail chunk (or a misaligned stream) is staged with plain loads;
