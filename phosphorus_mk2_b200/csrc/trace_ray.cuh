@@ -78,7 +78,12 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 #else
-  return 1.0f / x;
+  float r = 1.0f / x;
+#ifdef PHOS_EMUL_RCP_PERTURB  // host emulation only (tests/emul): the worst a 1-ulp reciprocal may return, either way
+  static unsigned toggle = 0;
+  r = nextafterf(r, (toggle++ & 1u) ? INFINITY : -INFINITY);
+#endif
+  return r;
 #endif
 }
 

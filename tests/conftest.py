@@ -41,13 +41,10 @@ def reflib():
     return RefLib()
 
 
-@pytest.fixture(scope="session")
-def emul():
-    """Host emulation of the device traversal source (tests/emul), built on demand."""
+def _build_emul(defs):
     import ctypes as C
     from phosphorus_mk2_b200.rays import PhosRays
     here = os.path.join(ROOT, "tests", "emul")
-    defs = os.environ.get("PHOS_EMUL_DEFS", "").split()  # e.g. "-DPHOS_SIGN_HITS=0": emulate a kernel build knob
     tag = "".join(c if c.isalnum() else "_" for c in "".join(defs))
     so = os.path.join(here, f"libemul_trace{tag}.so")
     srcs = [os.path.join(here, "emul_trace.cpp"), os.path.join(ROOT, "phosphorus_mk2_b200", "csrc", "repack.cpp")]
@@ -60,6 +57,20 @@ def emul():
                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_char_p]
     L.emul_repack_digest.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     return L
+
+
+@pytest.fixture(scope="session")
+def emul():
+    """Host emulation of the device traversal source (tests/emul), built on demand.  PHOS_EMUL_DEFS (e.g.
+    "-DPHOS_X=1") emulates a kernel build knob."""
+    return _build_emul(os.environ.get("PHOS_EMUL_DEFS", "").split())
+
+
+@pytest.fixture(scope="session")
+def emul_rcp():
+    """The same emulation with every reciprocal direction pushed one ulp off, alternately up and down: the worst the
+    device's MUFU.RCP may return.  Results must not change (the box test is conservative by more than that)."""
+    return _build_emul(["-DPHOS_EMUL_RCP_PERTURB"])
 
 
 @pytest.fixture(scope="session")
