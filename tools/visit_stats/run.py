@@ -14,7 +14,7 @@ so = os.path.join(HERE, "libstats.so")
 subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I/usr/local/cuda/include",
                 os.path.join(HERE, "stats.cpp"), os.path.join(ROOT, "phosphorus_mk2_b200", "csrc", "repack.cpp"), "-o", so], check=True)
 L = C.CDLL(so)
-L.visit_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(PhosRays), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+L.visit_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(PhosRays), C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]
 which = sys.argv[1]
 sc = scenes.sphere_field() if which == "spheres" else scenes.terrain(n=700)
 a = Accel(sc); nodes, packets = a.nodes_array(), a.packets_array()
@@ -43,7 +43,12 @@ for sname, rays in sets.items():
     base = None
     for mode in (0, 1, 2, 4):
         rb = rays.copy(); s = rb.as_struct(); out = (C.c_uint64 * 4)()
-        assert L.visit_stats(nodes.ctypes.data, len(nodes) // 288, packets.ctypes.data, len(packets) // 384, C.byref(s), rb.n, mode, out) == 0
+        per = np.zeros(rb.n, np.uint32) if mode == 0 else None
+        assert L.visit_stats(nodes.ctypes.data, len(nodes) // 288, packets.ctypes.data, len(packets) // 384, C.byref(s), rb.n, mode, out,
+                             per.ctypes.data if per is not None else None) == 0
         v, nh, sk, h = list(out)
         if base is None: base = v
+        if per is not None:
+            q = np.percentile(per, [50, 90, 99, 99.9, 100])
+            print(f"{which:8s} {sname:7s} node visits per ray: mean {per.mean():.1f}, median {q[0]:.0f}, p90 {q[1]:.0f}, p99 {q[2]:.0f}, p99.9 {q[3]:.0f}, max {q[4]:.0f}", flush=True)
         print(f"{which:8s} {sname:7s} {names[mode]:20s} visits/ray {v/rb.n:6.2f} ({100*v/base:5.1f} %)  no-hit visits {100*nh/v:4.1f} %  skipped {sk/rb.n:5.2f}/ray  hits {h}", flush=True)

@@ -50,7 +50,8 @@ struct Entry { uint2 g; float bound; float back_bound; float ctn[8]; };
 // mode 0: baseline; 1: exact group bound (min tn over remaining hit inner children); 2: back-half bound over hit inner+leaf;
 // 3: back-half bound inner only; 4: per-child distances (ideal)
 extern "C" int visit_stats(const void* nodes288, uint32_t n_nodes, const void* packets384, uint32_t n_packets, const phos_rays* rays,
-                           uint64_t n, int mode, uint64_t* out /* visits, nohit visits, skipped groups/children, hits */) {
+                           uint64_t n, int mode, uint64_t* out /* visits, nohit visits, skipped groups/children, hits */,
+                           uint32_t* per_ray /* node visits of every ray, or null */) {
   static PackedAccel packed; static bool have = false;
   std::string e;
   if (!have) { if (!repack_accel((const RefNode*)nodes288, n_nodes, (const RefPacket*)packets384, n_packets, packed, e)) return 1; have = true; }
@@ -64,6 +65,7 @@ extern "C" int visit_stats(const void* nodes288, uint32_t n_nodes, const void* p
     Entry st[64]; int sp = 0;
     Entry cur; cur.g = make_uint2(0u, 1u | ((1u << rd.oct) << 8)); cur.bound = 0; cur.back_bound = 0; for (int k = 0; k < 8; ++k) cur.ctn[k] = 0;
     bool done = false;
+    const uint64_t visits_before = visits;
     while (!done) {
       if ((cur.g.y >> 8) == 0u) { if (sp == 0) break; cur = st[--sp];
         if (mode == 1 && cur.bound > r.d) { ++skipped; cur.g.y &= 0xffu; continue; }
@@ -96,6 +98,7 @@ extern "C" int visit_stats(const void* nodes288, uint32_t n_nodes, const void* p
       cur = nx;
     }
     if (r.flags & PHOS_HIT) ++hits;
+    if (per_ray) per_ray[i] = (uint32_t)(visits - visits_before);
   }
   out[0] = visits; out[1] = nohit; out[2] = skipped; out[3] = hits;
   return 0;
