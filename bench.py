@@ -1,19 +1,30 @@
 #!/usr/bin/env python3
-"""bench.py — the ray-query benchmark (BASELINE.json metric: Mrays/s).
+"""bench.py — the ray-query / path-tracing benchmark (BASELINE.json metric: Mrays/s and samples/s).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spheres|terrain|cornell] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--only headline,config1,config3,config4,config5]
 
-A step = one pass of the hot path (closest-hit traversal of one frame's worth of rays) over one
-batch of synthetic rays.  Default workload = BASELINE.json configs[1]: the procedural 1 048 576-
-triangle sphere field, 1920 x 1080 coherent primary rays generated on the device by the camera
-kernel in the reference's 32 x 32 tile order, closest hit only.
-
-Prints ONE JSON line (rank 0).  `value` is whole-job Mrays/s with the ray stream resident in HBM,
-timed with CUDA events around the traversal kernel (L2 flushed and rays regenerated, untimed, before
-every step); `e2e` is the same metric through the C ABI with page-locked HOST ray arrays, copies
-inside the timed region; `roofline` relates the traversal kernel to the measured HBM bandwidth using
-the oracle's per-ray node / triangle counts; `cpu_baseline` is the reference's own stream kernel
+Prints ONE JSON line (rank 0).  The headline (`metric`, `value`, `e2e`, `roofline`, `cpu_baseline`) is
+BASELINE.json configs[1]: the procedural 1 048 576-triangle sphere field, 1920 x 1080 coherent primary rays
+generated on the device in the reference's 32 x 32 tile order, closest hit only.  A step = one pass of the hot
+path (closest-hit traversal of one frame's worth of rays).  `value` is whole-job Mrays/s with the ray stream
+resident in HBM, timed with CUDA events around the traversal kernel (L2 flushed and rays regenerated, untimed,
+before every step); `e2e` is the same metric through the C ABI with page-locked HOST ray arrays, copies inside
+the timed region; `roofline` relates the traversal kernel to the measured HBM bandwidth using the oracle's
+per-ray node / triangle counts and adds the issue-slot view (warp-level step counters of the same
+launch, instruction weights from the committed ncu capture); `cpu_baseline` is the reference's own stream kernel
 (oracle/_ref, compiled from the reference sources) on all host threads over the same rays.
+
+`configs` holds the other BASELINE configurations, measured in the same run:
+  config1_cornell   Cornell box 512 x 512: primary + next-event shadow rays (Mrays/s) and the 64 spp frame (samples/s)
+  config3_bounce /  10 M-triangle terrain: the BSDF-sampled bounce-ray stream and the next-event shadow-ray stream of
+  config3_shadow    a 1920 x 1080 frame, produced by the pipeline itself: Mrays/s, roofline, parity over EVERY ray
+  config4_frame     depth-8 path trace, 64 spp, 1920 x 1080, diffuse + 10 % GGX: samples/s; with --gpus N the frame is
+                    tile-partitioned over the ranks and the film is reduced with ONE NCCL reduce per frame INSIDE
+                    the timed region (strong scaling)
+  config5_frame     (--gpus N > 1 only) 30 M-triangle instanced field at 3840 x 2160, sample-partitioned: every rank
+                    renders 16 samples of every pixel, one NCCL reduce of the 132.7 MB film per frame
+CPU baselines (reference stream kernel / reference cpu_t renderer from oracle/_ref) are taken on rank 0 at N = 1
+only, on bounded samples stated in each record.
 """
 from __future__ import annotations
 
@@ -31,25 +42,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from phosphorus_mk2_b200 import scenes  # noqa: E402
-from phosphorus_mk2_b200.rays import HIT, RayBatch  # noqa: E402
+from phosphorus_mk2_b200.rays import HIT, MASKED, SHADOW, RayBatch  # noqa: E402
 
 S_NODE, S_TRI = 80, 48  # bytes of a packed node / triangle (csrc/phos_internal.hpp)
 B_IO_CLOSEST = 56       # 32 B read (p, wi, d, flags) + 24 B written (d, flags, mesh, face, u, v) per ray
+B_IO_ANY = 40           # 32 B read + 8 B written (d, flags) per occlusion query
+FIELDS = ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags")
+TILE = 32
+
+LABELS = {
+    "spheres": "configs[1]: procedural 1M-triangle tessellated sphere field, 1920x1080 coherent primary rays, closest-hit",
+    "terrain": "configs[2]: procedural 10M-triangle displaced terrain, 1920x1080, bounce + shadow ray streams of the frame",
+    "terrain_ggx": "configs[3]: 10M-triangle terrain, diffuse + 10% GGX (roughness 0.2) face bands, sky emitter, 1920x1080",
+    "instanced30m": "configs[4]: 30M-triangle field of baked copies of one 4096-triangle object, 3840x2160",
+    "cornell": "configs[0]: synthetic Cornell box (38 tris, 2 area lights) 512x512",
+    "tiny": "tiny smoke workload (4x4 spheres, 256x256)",
+}
 
 
 def make_workload(name: str):
     if name == "spheres":
-        return scenes.sphere_field(), "configs[1]: procedural 1M-triangle tessellated sphere field, 1920x1080 coherent primary rays, closest-hit"
+        return scenes.sphere_field(), LABELS[name]
     if name == "terrain":
-        return scenes.terrain(), "configs[2] geometry: procedural 10M-triangle displaced terrain, 1920x1080 primary rays, closest-hit"
+        return scenes.terrain(), LABELS[name]
     if name == "terrain_ggx":
-        return scenes.terrain(glossy_fraction=0.1), "configs[3]: 10M-triangle terrain, diffuse + 10% GGX (roughness 0.2) face bands, sky emitter, 1920x1080"
+        return scenes.terrain(glossy_fraction=0.1), LABELS[name]
     if name == "instanced30m":
-        return scenes.instanced_field(), "configs[4]: 30M-triangle field of baked copies of one 4096-triangle object, 3840x2160"
+        return scenes.instanced_field(), LABELS[name]
     if name == "cornell":
-        return scenes.cornell_box(), "configs[0]: synthetic Cornell box 512x512 primary rays, closest-hit"
+        return scenes.cornell_box(), LABELS[name]
     if name == "tiny":
-        return scenes.sphere_field(4, 16, 8, 256, 256), "tiny smoke workload (4x4 spheres, 256x256)"
+        return scenes.sphere_field(4, 16, 8, 256, 256), LABELS[name]
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -58,6 +81,16 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def capture_table():
+    """profiles/ncu_capture.json: per workload, figures of the committed `ncu --set full` capture of trace_kernel
+    (DRAM bytes per launch) and the instruction weights of the issue model (warp instructions per node step /
+    triangle step / loop iteration / ray, fitted to smsp__inst_executed.sum of those captures)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_capture.json")))
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -99,12 +132,34 @@ class ClockSampler:
 
 
 def tile_order_tiles(cam):
-    from phosphorus_mk2_b200.device import make_tiles
-    return make_tiles(cam.film_width, cam.film_height, 32)
+    """job::tiles_t::make (src/jobs/tiles.hpp:49-89) — restated here so the reference arm imports no product code."""
+    W, H = cam.film_width, cam.film_height
+    return [(x, y, min(TILE, W - x), min(TILE, H - y)) for y in range(0, H, TILE) for x in range(0, W, TILE)]
 
 
+def copy_batch(src: RayBatch, lo: int = 0, hi: int | None = None) -> RayBatch:
+    hi = src.n if hi is None else hi
+    out = RayBatch(hi - lo)
+    for f in FIELDS:
+        getattr(out, f)[:] = getattr(src, f)[lo:hi]
+    return out
+
+
+def headline_config(label, n, triangles):
+    """The `config` both arms print (same keys, same values: the workload, not the implementation)."""
+    return {"workload": label, "rays_per_step_per_gpu": n, "triangles": triangles,
+            "l2": "GPU arm: flushed (256 MiB memset) and rays regenerated before every timed step; CPU arm: n/a",
+            "timing": "GPU arm: CUDA events around the traversal kernel, summed over steps, max over ranks; CPU arm: wall clock inside ref_trace"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args, scene, label):
-    """The reference's own CPU implementation of the path (oracle/_ref), all host threads."""
+    """The reference's own CPU implementation of the path (oracle/_ref), all host threads.  The timed region is the
+    unmodified stream_mbvh_kernel_t::trace on 1024-ray streams pulled from an atomic cursor (the shape of
+    cpu.cpp:223-238) plus the memcpys that cut the flat arrays into ray_t<1024> and back (72 B per ray: a few per cent
+    of a stream's time, charged to the reference)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -128,6 +183,9 @@ def run_reference_arm(args, scene, label):
         def step():
             return rs.trace(rays, "stream", threads=cores)[1]
     else:
+        # oracle/_ref is built from /root/reference in the build container and travels to the GPU box; without it the
+        # plain-C restatement of the traversal is timed instead (one thread), on the tree of the library's host builder
+        # (bit-identical to the reference builder; the only product code this arm would then touch, and only here)
         from phosphorus_mk2_b200.device import Accel
         acc = Accel(scene)
         build_s = acc.build_seconds
@@ -146,156 +204,153 @@ def run_reference_arm(args, scene, label):
     line = {"impl": "reference", "metric": "Mrays/s (closest-hit)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "rays_per_step": rays.n, "triangles": scene.num_triangles()},
+            "config": headline_config(label, rays.n, scene.num_triangles()),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind,
                              "sample": f"whole frame ({rays.n} rays) per step, reference stream_mbvh_kernel_t, {cores} threads; "
-                                       f"BVH build {build_s:.2f} s excluded"},
+                                       f"BVH build {build_s:.2f} s excluded; flat arrays <-> ray_t<1024> memcpys (72 B/ray) included"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_render_bench(args, scene, label):
-    """Path-traced samples/s: a step = one frame of --spp samples per pixel at --depth, the frame split
-    over the ranks by tiles (or sample ranges), one NCCL film reduce per frame inside the timed region."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    cam = scene.camera
-    n_px = cam.film_width * cam.film_height
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        from oracle.pyoracle import RefLib
-        ref = RefLib()
-        rs = ref.scene(scene)
-        spp = 4 if n_px > 512 * 512 else 16  # bounded sample: the CPU renderer at a reduced, perfect-square spp
-        secs = []
-        for i in range(args.warmup + args.steps):
-            _, s_ = rs.render(spp, 1, args.depth, single_threaded=False)
-            if i >= args.warmup:
-                secs.append(s_)
-        v = n_px * spp * len(secs) / sum(secs)
-        print(json.dumps({"impl": "reference", "metric": "path-traced samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": label, "spp": spp, "depth": args.depth, "pixels": n_px},
-                          "cpu_baseline": {"value": v, "unit": "samples/s", "cores": ref.hardware_concurrency(), "kind": "reference",
-                                           "sample": f"{spp} spp frame (reference cpu_t::start/join, all host threads)"},
-                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
-        return
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
-    from phosphorus_mk2_b200.frame import film_tensor, reduce_film, samples_of_rank, tiles_of_rank
-    dev = CudaDevice.make(Options(samples_per_pixel=args.spp, paths_per_sample=1, path_depth=args.depth), local)
-    acc = Accel(scene)
-    dev.preprocess(scene, acc)
-    dev.upload_scene(scene)
-    tiles = tile_order_tiles(cam)
-    if args.partition == "tiles":
-        my_tiles, my_range = tiles_of_rank(tiles, rank, world), (0, args.spp)
-    else:
-        my_tiles, my_range = tiles, samples_of_rank(args.spp, rank, world)
-    film_t = film_tensor(dev) if dist else None
+# ---------------------------------------------------------------------------------------------------------------
+# helpers of the GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class Run:
+    """Process-wide state of the GPU arm."""
 
-    def frame(read_back: bool):
-        dev.film_clear()
-        if my_range[1] > my_range[0] and my_tiles:
-            dev.render(my_tiles, my_range[0], my_range[1], args.spp, seed=1)
-        dev.synchronize()
-        if dist:
-            reduce_film(film_t, dist, 0)
+    def __init__(self, args):
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.torch = None
+        if self.world > 1:
             import torch
-            torch.cuda.synchronize()
-        if read_back and rank == 0:
-            return dev.film_read()
-        return None
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist, self.torch = dist, torch
+        self.cpu_legs = self.rank == 0 and self.world == 1 and not args.no_cpu_baseline
+        self.capture = capture_table()
+        self.sm_count = 148
+        self.sm_mhz = 1965.0
+        self._ref = None
 
-    for _ in range(args.warmup):
-        frame(False)
-    if dist:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = dev.launch_count()
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max_over_ranks(self, *vals):
+        if not self.dist:
+            return vals if len(vals) > 1 else vals[0]
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        out = tuple(float(x) for x in t)
+        return out if len(out) > 1 else out[0]
+
+    def reflib(self):
+        if self._ref is None:
+            from oracle.pyoracle import RefLib
+            self._ref = RefLib() if RefLib.available() else False
+        return self._ref or None
+
+
+def issue_figures(run: Run, workload: str, prof: dict, ms: float):
+    """The issue-slot view of one traversal launch: warp instructions (from the warp-level step counters of the counting
+    instantiation on the same rays, weighted with the per-step instruction counts fitted to the committed ncu capture)
+    against what 148 SMs x 4 schedulers can issue in the measured time, and the lanes that do useful work per step."""
+    w = dict(run.capture.get("issue_model", {}))
+    i_node, i_tri = w.get("node_step", 240.0), w.get("tri_step", 175.0)
+    i_iter, i_ray = w.get("loop_iteration", 22.0), w.get("per_ray_warp", 4.0)
+    warp_instr = i_node * prof["warp_node_steps"] + i_tri * prof["warp_tri_steps"] + i_iter * prof["warp_iterations"] + i_ray * prof["rays"]
+    slots = run.sm_count * 4 * run.sm_mhz * 1e6 * ms * 1e-3
+    step_instr = i_node * prof["warp_node_steps"] + i_tri * prof["warp_tri_steps"]
+    lanes = (i_node * prof["lanes_node_steps"] + i_tri * prof["lanes_tri_steps"]) / max(step_instr, 1.0)
+    return {"issue_frac": warp_instr / slots, "warp_instructions_per_launch": warp_instr,
+            "lanes_per_instruction": lanes,
+            "lanes_per_node_step": prof["lanes_node_steps"] / max(prof["warp_node_steps"], 1),
+            "lanes_per_tri_step": prof["lanes_tri_steps"] / max(prof["warp_tri_steps"], 1),
+            "issue_source": "in-run warp-step counters x instruction weights of profiles/ncu_capture.json; "
+                            f"{run.sm_count} SMs x 4 schedulers x {run.sm_mhz:.0f} MHz",
+            "ncu_capture": run.capture.get(workload)}
+
+
+def roofline(run: Run, workload: str, n_rays: int, ms: float, n_node: float, n_tri: float, b_io: int, prof: dict | None):
+    peak, peak_src = peaks()
+    b_ray = b_io + n_node * S_NODE + n_tri * S_TRI
+    achieved = n_rays * b_ray / (ms * 1e-3) / 1e9
+    cap = run.capture.get(workload) or {}
+    out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "traffic": cap.get("dram_bytes_per_launch"),
+           "traffic_source": (f"ncu --set full capture {cap.get('capture')} of this workload (not this run)" if cap.get("dram_bytes_per_launch") else None),
+           "algorithmic_bytes_per_launch": n_rays * b_ray, "kernel": "trace_kernel", "peak_source": peak_src,
+           "bytes_per_ray": b_ray, "oracle_nodes_per_ray": n_node, "oracle_tris_per_ray": n_tri}
+    if prof:
+        traced = max(prof["rays"], 1)
+        out.update({"gpu_nodes_per_ray": prof["nodes"] / traced, "gpu_tris_per_ray": prof["tris"] / traced,
+                    "gpu_fetched_bytes_per_ray": b_io + (prof["nodes"] * S_NODE + prof["tris"] * S_TRI) / traced})
+        out["gpu_fetched_frac"] = n_rays * out["gpu_fetched_bytes_per_ray"] / (ms * 1e-3) / 1e9 / peak
+        out.update(issue_figures(run, workload, prof, ms))
+    return out
+
+
+def time_stream(dev, dr, fresh, n, steps):
+    """Mean milliseconds of the traversal kernel over `steps` launches on the first n rays of dr (CUDA events; L2 flushed
+    and the stream restored, untimed, before every launch; 3 untimed launches first)."""
+    ms = []
+    for i in range(3 + steps):
+        dev.flush_l2()
+        fresh()
+        dev.timer_begin()
+        dev.trace_device_n(dr, n)
+        t = dev.timer_end()
+        if i >= 3:
+            ms.append(t)
+    return float(np.mean(ms)), float(np.min(ms))
+
+
+def stream_parity(orc, nodes, packets, rays_in: RayBatch, got: RayBatch):
+    """Every ray against the oracle traversal of the reference tree; returns (parity record, oracle counters)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity import mismatches
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        frame(False)
-    if dist:
-        dist.barrier()
-    dt = time.perf_counter() - t0
-    launches = dev.launch_count() - l0
-    t0 = time.perf_counter()
-    img = None
-    for _ in range(max(1, args.steps // 2)):
-        img = frame(True)
-    if dist:
-        dist.barrier()
-    dt_e2e = (time.perf_counter() - t0) / max(1, args.steps // 2)
-    if dist:
-        import torch
-        t = torch.tensor([dt, dt_e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, dt_e2e = float(t[0]), float(t[1])
-    clocks = sampler.stop() if rank == 0 else None
-    if rank == 0:
-        v = n_px * args.spp * args.steps / dt
-        print(json.dumps({"metric": "path-traced samples/s", "value": v, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": label, "spp": args.spp, "depth": args.depth, "pixels": n_px, "partition": args.partition,
-                                     "timing": "wall clock around K frames (render + NCCL film reduce), barrier + sync both sides"},
-                          "clocks": clocks, "gpu_launches": int(launches),
-                          "e2e": {"value": n_px * args.spp / dt_e2e, "unit": "samples/s", "h2d_bytes_per_step": 16 * len(my_tiles) + 8 * args.spp,
-                                  "d2h_bytes_per_step": 16 * n_px},
-                          "image_mean": float(img[..., :3].mean()) if img is not None else None}), flush=True)
-    dev.close()
-    if dist:
-        dist.destroy_process_group()
+    want, cnt = orc.traverse(nodes, packets, rays_in)
+    secs = time.perf_counter() - t0
+    bad = mismatches(rays_in, got, want)
+    return {"rays": int(rays_in.n), "mismatch_vs_oracle": int(len(bad)), "oracle_seconds": secs}, cnt
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="spheres")
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--render", action="store_true", help="path-traced samples/s (BASELINE configs[0]/[3]) instead of Mrays/s")
-    ap.add_argument("--spp", type=int, default=16)
-    ap.add_argument("--depth", type=int, default=8)
-    ap.add_argument("--partition", default="tiles", choices=["tiles", "samples"])
-    args = ap.parse_args()
-    if args.impl != "reference" and not args.render:
-        args.warmup = max(args.warmup, 3)  # timing hygiene for the kernel metric; frame benches take what they are given
+def reference_stream_leg(run: Run, rs, rays_in: RayBatch, got: RayBatch, traced: int, budget_s: float = 8.0):
+    """The reference's stream kernel on the same rays, all host threads: cpu_baseline + how its results differ from the
+    exact ones (false misses / farther hits of its 12-bit-reciprocal slab test, ties)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity import classify_vs_stream
+    ref = run.reflib()
+    cores = ref.hardware_concurrency()
+    out, s1 = rs.trace(rays_in, "stream", threads=cores)  # calibration pass; its results are classified
+    reps = int(max(1, min(40, budget_s / max(s1, 1e-3))))
+    secs = sum(rs.trace(rays_in, "stream", threads=cores)[1] for _ in range(reps))
+    missed, farther, tied, other = classify_vs_stream(rays_in, out, got)
+    shadow = (rays_in.flags & SHADOW) != 0
+    masked = (rays_in.flags & MASKED) != 0
+    verdict = int(((out.flags & HIT) != (got.flags & HIT))[shadow & ~masked].sum())
+    cpu = {"value": traced * reps / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+           "sample": f"the same {rays_in.n}-ray stream x {reps} passes ({secs:.1f} s), reference stream_mbvh_kernel_t on {cores} threads, "
+                     f"reference BVH build {rs.build_seconds:.2f} s excluded"}
+    vs = {"rays": int(rays_in.n), "stream_missed": int(len(missed)), "stream_farther": int(len(farther)), "tied": int(len(tied)),
+          "other": int(len(other)), "shadow_verdict_differs": verdict,
+          "note": "reference stream kernel (12-bit rcp slab test) vs this library on the same rays; this library == exact oracle"}
+    return cpu, vs
 
-    scene, label = make_workload(args.workload)
-    if args.render:
-        run_render_bench(args, scene, label)
-        return
-    if args.impl == "reference":
-        run_reference_arm(args, scene, label)
-        return
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
+# ---------------------------------------------------------------------------------------------------------------
+# headline: config 2
+# ---------------------------------------------------------------------------------------------------------------
+def headline(run: Run, scene, label):
     from phosphorus_mk2_b200.device import Accel, CudaDevice, Options, pinned_ray_batch
-
-    dev = CudaDevice.make(Options(), local)  # raises without the library or a GPU: no fallback
+    args, rank, world = run.args, run.rank, run.world
+    dev = CudaDevice.make(Options(), run.local)  # raises without the library or a GPU: no fallback
     t0 = time.perf_counter()
     acc = Accel(scene)
     dev.preprocess(scene, acc)
@@ -321,54 +376,39 @@ def main():
 
     for _ in range(args.warmup):
         dev_step(False)
-    if dist:
-        dist.barrier()
+    run.barrier()
     dev.synchronize()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(run.local)
     if rank == 0:
         sampler.start()
     launches0 = dev.launch_count()
     wall0 = time.perf_counter()
     step_ms = [dev_step(True) for _ in range(args.steps)]
     dev.synchronize()
-    if dist:
-        dist.barrier()
+    run.barrier()
     wall = time.perf_counter() - wall0
     launches = dev.launch_count() - launches0
-    total_ms = float(sum(step_ms))
-    if dist:
-        import torch
-        t = torch.tensor([total_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = run.max_over_ranks(float(sum(step_ms)))
     clocks = sampler.stop() if rank == 0 else None
+    if clocks and clocks.get("sm_mhz"):
+        run.sm_mhz = clocks["sm_mhz"]
     value = world * n * args.steps / (total_ms * 1e-3) / 1e6
 
-    # GPU's own fetch counts for the same batch (for the record; the roofline uses the oracle's counts)
+    # the GPU's own fetch counts and warp-level step statistics for the same batch
     dev.camera_rays(tiles, drays)
-    g_nodes, g_tris = dev.trace_count(drays)
+    prof = dev.trace_profile(drays)
     result = drays.download()
     hits = int(result.hit.sum())
 
     # ---- the same frame as occlusion queries (BASELINE metric "closest-hit, shadow"): any-hit Mrays/s ------------
-    # SHADOW set on every camera ray (tmax = FLT_MAX): the traversal stops at the first accepted triangle.  Rank 0.
     any_hit = None
     if rank == 0:
-        from phosphorus_mk2_b200.rays import SHADOW
         dev.camera_rays(tiles, drays)
         shadow_host = drays.download()
         shadow_host.flags[:] = SHADOW
-        ms = []
-        for i in range(3 + max(3, min(args.steps, 10))):
-            dev.flush_l2()
-            drays.upload(shadow_host)
-            dev.timer_begin()
-            dev.trace_device(drays)
-            t = dev.timer_end()
-            if i >= 3:
-                ms.append(t)
+        ms, _ = time_stream(dev, drays, lambda: drays.upload(shadow_host), n, max(3, min(args.steps, 10)))
         occluded = drays.download()
-        any_hit = {"value": n / (float(np.mean(ms)) * 1e-3) / 1e6, "unit": "Mrays/s", "rays": n,
+        any_hit = {"value": n / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "rays": n,
                    "occluded_fraction": float(occluded.hit.mean()), "verdict_equals_closest_hit": bool(np.array_equal(occluded.hit, result.hit))}
 
     # ---- end to end through the C ABI with pinned host arrays: e2e ------------------------------------
@@ -376,12 +416,11 @@ def main():
     pristine = drays.download()
     # one rank per GPU: stay on the CPUs next to this GPU before allocating the page-locked arrays (first touch),
     # so the up-copies and the zero-copy result stores do not cross the socket interconnect
-    numa_cpus = dev._L.phos_cuda_bind_host_to_device(local)
+    numa_cpus = dev._L.phos_cuda_bind_host_to_device(run.local)
     hrays = pinned_ray_batch(n)
-    fields = ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags")
 
     def restore():
-        for f in fields:
+        for f in FIELDS:
             getattr(hrays, f)[:] = getattr(pristine, f)
 
     for _ in range(2):
@@ -391,92 +430,361 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(e2e_steps):
         restore()
-        if dist:
-            dist.barrier()
+        run.barrier()
         t1 = time.perf_counter()
         dev.trace(hrays)  # blocking: H2D + traversal + D2H
         e2e_s += time.perf_counter() - t1
-    if dist:
-        import torch
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = run.max_over_ranks(e2e_s)
     e2e = world * n * e2e_steps / e2e_s / 1e6
     e2e_ok = bool(np.array_equal(hrays.flags, result.flags) and np.array_equal(hrays.d.view(np.uint32), result.d.view(np.uint32)))
+    hrays.free()
 
     # ---- CPU baseline + oracle counts (rank 0, N = 1 only) ------------------------------------------
-    cpu = None
-    roof = None
-    parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.pyoracle import Oracle, RefLib  # the checker / CPU baseline leg only
+    cpu = roof = parity = None
+    if run.cpu_legs:
+        from oracle.pyoracle import Oracle  # the checker / CPU baseline leg only
         orc = Oracle()
         nodes, packets = acc.nodes_array(), acc.packets_array()
         # oracle traversal of EVERY ray of the frame (a few seconds): per-ray node / triangle counts for the
         # roofline, and the parity verdict of the whole batch
-        sel = np.arange(n)
-        sample = RayBatch(len(sel))
-        for f in fields:
-            getattr(sample, f)[:] = getattr(pristine, f)[sel]
-        want, cnt = orc.traverse(nodes, packets, sample)
-        n_node, n_tri = cnt.nodes / cnt.rays, cnt.triangles / cnt.rays
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from parity import mismatches
-        got = RayBatch(len(sel))
-        for f in fields:
-            getattr(got, f)[:] = getattr(result, f)[sel]
-        parity = {"sample_rays": int(len(sel)), "mismatch_vs_oracle": int(len(mismatches(sample, got, want)))}
-        b_ray = B_IO_CLOSEST + n_node * S_NODE + n_tri * S_TRI
-        peak, peak_src = peaks()
-        ms_kernel = total_ms / args.steps
-        achieved = n * b_ray / (ms_kernel * 1e-3) / 1e9
-        traffic = None  # DRAM bytes per launch from the committed ncu capture of this workload, if there is one
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
-        except Exception:
-            pass
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch": n * b_ray,
-                "kernel": "trace_kernel", "peak_source": peak_src, "bytes_per_ray": b_ray,
-                "oracle_nodes_per_ray": n_node, "oracle_tris_per_ray": n_tri,
-                "gpu_fetched_bytes_per_ray": B_IO_CLOSEST + (g_nodes * S_NODE + g_tris * S_TRI) / n,
-                "gpu_nodes_per_ray": g_nodes / n, "gpu_tris_per_ray": g_tris / n}
-        if RefLib.available():
-            ref = RefLib()
-            rs = ref.scene(scene)
-            build_s = rs.build()
-            cores = ref.hardware_concurrency()
-            _, s1 = rs.trace(pristine, "stream", threads=cores)       # calibration / warm-up pass
-            reps = int(max(1, min(40, 10.0 / max(s1, 1e-3))))
-            secs = sum(rs.trace(pristine, "stream", threads=cores)[1] for _ in range(reps))
-            cpu = {"value": n * reps / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
-                   "sample": f"the same {n}-ray frame x {reps} passes ({secs:.1f} s), reference stream_mbvh_kernel_t on {cores} threads, "
-                             f"reference BVH build {build_s:.2f} s excluded"}
+        parity, cnt = stream_parity(orc, nodes, packets, pristine, result)
+        roof = roofline(run, "spheres", n, total_ms / args.steps, cnt.nodes / cnt.rays, cnt.triangles / cnt.rays, B_IO_CLOSEST, prof)
+        if run.reflib():
+            rs = run.reflib().scene(scene)
+            rs.build()
+            cpu, vs = reference_stream_leg(run, rs, pristine, result, n, budget_s=10.0)
+            parity["vs_reference_stream"] = vs
         else:
             t1 = time.perf_counter()
-            orc.traverse(nodes, packets, sample)
+            orc.traverse(nodes, packets, pristine)
             secs = time.perf_counter() - t1
-            cpu = {"value": len(sel) / secs / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
-                   "sample": f"the whole {len(sel)}-ray frame once, scalar oracle traversal"}
-
-    if rank == 0:
-        line = {"metric": "Mrays/s (closest-hit)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": label, "rays_per_step_per_gpu": n, "triangles": scene.num_triangles(),
-                           "packed_nodes": st.nodes, "packed_bytes": int(st.bytes_nodes + st.bytes_triangles),
-                           "l2": "flushed (256 MiB memset) and rays regenerated before every timed step",
-                           "timing": "CUDA events around the traversal kernel, summed over steps, max over ranks",
-                           "hit_fraction": hits / n, "preprocess_s": prep_s, "wall_s_timed_loop": wall},
-                "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 8 * n + 16 * hits,
-                        "steps": e2e_steps, "matches_device_path": e2e_ok, "host_cpus_bound": numa_cpus},
-                "any_hit": any_hit,
-                "roofline": roof, "cpu_baseline": cpu, "parity": parity}
-        print(json.dumps(line), flush=True)
+            cpu = {"value": n / secs / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+                   "sample": f"the whole {n}-ray frame once, scalar oracle traversal"}
+    drays.free()
     dev.close()
-    if dist:
-        dist.destroy_process_group()
+
+    line = {"metric": "Mrays/s (closest-hit)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": headline_config(label, n, scene.num_triangles()),
+            "details": {"packed_nodes": st.nodes, "packed_bytes": int(st.bytes_nodes + st.bytes_triangles),
+                        "hit_fraction": hits / n, "preprocess_s": prep_s, "wall_s_timed_loop": wall},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 8 * n + 16 * hits,
+                    "steps": e2e_steps, "matches_device_path": e2e_ok, "host_cpus_bound": numa_cpus},
+            "any_hit": any_hit,
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity}
+    return line
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ray streams of a frame (configs 1 and 3)
+# ---------------------------------------------------------------------------------------------------------------
+def frame_streams(run: Run, dev, acc, scene, workload: str, streams=("primary", "bounce", "shadow"), steps: int = 8,
+                  rs=None, orc=None):
+    """Mrays/s of the ray streams the pipeline itself produces for sample 0 of the frame: the primary rays, the
+    BSDF-sampled bounce rays from the primary hits (compacted) and the next-event shadow rays (one per primary slot,
+    SHADOW or SHADOW|MASKED).  With the CPU legs on: parity of EVERY ray against the oracle, the roofline from the
+    oracle's counts, and the reference stream kernel on the same rays."""
+    cam = scene.camera
+    tiles = tile_order_tiles(cam)
+    n = cam.film_width * cam.film_height
+    nodes = packets = None
+    if run.cpu_legs and orc is not None:
+        nodes, packets = acc.nodes_array(), acc.packets_array()
+    out = {}
+    for which in streams:
+        dr, src = dev.device_rays(n), dev.device_rays(n)
+        if which == "primary":
+            dev.camera_rays(tiles, src)
+            k = n
+        else:
+            k = dev.wavefront_rays(tiles, src, which, 0, 1, 42)
+        host = src.download()
+        src.free()
+        rays_in = copy_batch(host, 0, k)
+        traced = int(((rays_in.flags & MASKED) == 0).sum())
+        any_hit = which == "shadow"
+        ms, ms_min = time_stream(dev, dr, lambda: dr.upload(host), k, steps)
+        dr.upload(host)
+        prof = dev.trace_profile(dr, k)
+        got = copy_batch(dr.download(), 0, k)
+        rec = {"value": traced / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "rays": traced, "slots": int(k), "ms_per_launch": ms,
+               "best_launch_Mrays_s": traced / (ms_min * 1e-3) / 1e6, "query": "any-hit" if any_hit else "closest-hit",
+               "hit_fraction": float(got.hit[(rays_in.flags & MASKED) == 0].mean()) if traced else 0.0,
+               "l2": "flushed and stream restored before every timed launch", "launches_timed": steps}
+        if nodes is not None:
+            rec["parity"], cnt = stream_parity(orc, nodes, packets, rays_in, got)
+            rec["roofline"] = roofline(run, f"{workload}_{which}", traced, ms, cnt.nodes / max(cnt.rays, 1), cnt.triangles / max(cnt.rays, 1),
+                                       B_IO_ANY if any_hit else B_IO_CLOSEST, prof)
+            if rs is not None:
+                rec["cpu_baseline"], rec["parity"]["vs_reference_stream"] = reference_stream_leg(run, rs, rays_in, got, traced, budget_s=4.0)
+        else:
+            rec["issue"] = issue_figures(run, f"{workload}_{which}", prof, ms)
+        dr.free()
+        out[which] = rec
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# path-traced frames (configs 1, 4, 5)
+# ---------------------------------------------------------------------------------------------------------------
+def render_frames(run: Run, dev, scene, spp_total: int, depth: int, partition: str, steps: int, warmup: int):
+    """samples/s of whole frames: a step = one frame of spp_total samples per pixel, split over the ranks by tiles
+    (rank r renders tiles r, r + N, ...) or by sample ranges, ONE NCCL reduce of the film per frame inside the timed
+    region (N > 1).  `e2e` adds the read-back of the whole film into host memory on rank 0."""
+    from phosphorus_mk2_b200.frame import samples_of_rank, tiles_of_rank
+    cam = scene.camera
+    n_px = cam.film_width * cam.film_height
+    tiles = tile_order_tiles(cam)
+    rank, world, dist = run.rank, run.world, run.dist
+    if partition == "tiles":
+        my_tiles, my_range = tiles_of_rank(tiles, rank, world), (0, spp_total)
+    else:
+        my_tiles, my_range = tiles, samples_of_rank(spp_total, rank, world)
+    if dist and not dev.has_comm:
+        dev.comm_init(dist)  # the library's own NCCL communicator: rank 0's unique id shipped through torch.distributed
+
+    def frame(read_back: bool):
+        dev.film_clear()
+        if my_range[1] > my_range[0] and my_tiles:
+            dev.render(my_tiles, my_range[0], my_range[1], spp_total, seed=1)
+        if dist:
+            dev.film_reduce(0)  # ncclReduce on the library's stream, right behind the frame's kernels
+        dev.synchronize()
+        if read_back and rank == 0:
+            return dev.film_read()
+        return None
+
+    for _ in range(warmup):
+        frame(False)
+    run.barrier()
+    l0 = dev.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        frame(False)
+    run.barrier()
+    dt = time.perf_counter() - t0
+    launches = dev.launch_count() - l0
+    e2e_steps = max(1, steps // 2)
+    t0 = time.perf_counter()
+    img = None
+    for _ in range(e2e_steps):
+        img = frame(True)
+    run.barrier()
+    dt_e2e = (time.perf_counter() - t0) / e2e_steps
+    dt, dt_e2e = run.max_over_ranks(dt, dt_e2e)
+    return {"value": n_px * spp_total * steps / dt, "unit": "samples/s", "n_gpus": world, "scaling": "strong",
+            "ms_per_frame": 1e3 * dt / steps, "steps": steps, "warmup": warmup, "spp": spp_total, "depth": depth, "pixels": n_px,
+            "partition": partition,
+            "film_reduce": (f"phos_cuda_film_reduce: one ncclReduce(sum) of {16 * n_px} B to rank 0 per frame, inside the timed region" if dist else "single GPU: none"),
+            "timing": "wall clock around K frames (render + film reduce), barrier + device synchronize both sides, max over ranks",
+            "gpu_launches": int(launches),
+            "e2e": {"value": n_px * spp_total / dt_e2e, "unit": "samples/s", "h2d_bytes_per_step": 16 * len(my_tiles) + 8 * spp_total,
+                    "d2h_bytes_per_step": 16 * n_px},
+            "image_mean": float(img[..., :3].mean()) if img is not None else None}
+
+
+def reference_frame_leg(run: Run, scene, spp: int, depth: int):
+    """The reference renderer (cpu_t::preprocess / start / join from oracle/_ref) on a bounded sample: the same frame at a
+    reduced, perfect-square sample count, all host threads."""
+    ref = run.reflib()
+    if not ref:
+        return None
+    rs = ref.scene(scene)
+    cam = scene.camera
+    n_px = cam.film_width * cam.film_height
+    t0 = time.perf_counter()
+    _, secs = rs.render(spp, 1, depth, single_threaded=False)
+    wall = time.perf_counter() - t0
+    return {"value": n_px * spp / secs, "unit": "samples/s", "cores": ref.hardware_concurrency(), "kind": "reference",
+            "sample": f"the same frame at {spp} spp, depth {depth} ({secs:.1f} s in cpu_t::start..join, all host threads; "
+                      f"{wall - secs:.1f} s of scene set-up + reference BVH build excluded)"}
+
+
+def dropin_frame_leg(run: Run, scene, spp: int, depth: int):
+    """The frame as a user of the reference gets it: the reference's OWN host code (scene_t, job::tiles_t, sampler_t, a film_t
+    sink; oracle/_ref/libphos_ref_cuda.so) driving the drop-in cuda_t (integration/cuda.cpp) through make / preprocess /
+    start / join — wall clock around start..join like src/core.cpp:158-177, every tile handed to film_t::add_tile in host
+    memory.  The reference's single-threaded BVH build inside cuda_t::preprocess is outside that region, as it is for cpu_t."""
+    from oracle.pyoracle import RefLib
+    if not RefLib.available(cuda=True):
+        return None
+    ref = RefLib(cuda=True)
+    rs = ref.scene(scene)
+    cam = scene.camera
+    n_px = cam.film_width * cam.film_height
+    t0 = time.perf_counter()
+    img, secs = rs.render_cuda(spp, 1, depth)
+    wall = time.perf_counter() - t0
+    return {"value": n_px * spp / secs, "unit": "samples/s", "seconds_start_to_join": secs, "spp": spp, "depth": depth,
+            "h2d_bytes_per_step": 16 * len(tile_order_tiles(cam)), "d2h_bytes_per_step": 16 * n_px,
+            "image_mean": float(img[..., :3].mean()),
+            "how": f"reference host code -> cuda_t::start/join (guided tile claims, one film read-back per claim into page-locked memory, "
+                   f"add_tile per tile); {wall - secs:.1f} s of scene set-up + the reference's BVH build + upload excluded"}
+
+
+def config1(run: Run):
+    from oracle.pyoracle import Oracle
+    from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
+    scene = scenes.cornell_box()
+    dev = CudaDevice.make(Options(64, 1, 8), run.local)
+    acc = Accel(scene)
+    dev.preprocess(scene, acc)
+    dev.upload_scene(scene)
+    rs = None
+    if run.cpu_legs and run.reflib():
+        rs = run.reflib().scene(scene)
+        rs.build()
+    rec = {"workload": LABELS["cornell"]}
+    rec["streams"] = frame_streams(run, dev, acc, scene, "cornell", ("primary", "shadow"), steps=8, rs=rs, orc=Oracle() if run.cpu_legs else None)
+    rec["frame"] = render_frames(run, dev, scene, 64, 8, "tiles", steps=8, warmup=2)
+    if run.cpu_legs:
+        rec["frame"]["cpu_baseline"] = reference_frame_leg(run, scene, 16, 8)
+    dev.close()
+    return rec
+
+
+def config3(run: Run):
+    from oracle.pyoracle import Oracle
+    from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
+    scene = scenes.terrain()
+    dev = CudaDevice.make(Options(), run.local)
+    t0 = time.perf_counter()
+    acc = Accel(scene)
+    dev.preprocess(scene, acc)
+    dev.upload_scene(scene)
+    prep = time.perf_counter() - t0
+    rs = None
+    if run.cpu_legs and run.reflib():
+        rs = run.reflib().scene(scene)
+        rs.build()  # the reference's own single-threaded builder: ~20 s at 10 M triangles, excluded from every figure
+    st = dev.accel_stats()
+    rec = frame_streams(run, dev, acc, scene, "terrain", ("bounce", "shadow"), steps=8, rs=rs, orc=Oracle() if run.cpu_legs else None)
+    for r in rec.values():
+        r["workload"] = LABELS["terrain"]
+        r["triangles"] = scene.num_triangles()
+        r["packed_bytes"] = int(st.bytes_nodes + st.bytes_triangles)
+        r["preprocess_s"] = prep
+    dev.close()
+    return rec
+
+
+def config4(run: Run):
+    from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
+    scene = scenes.terrain(glossy_fraction=0.1)
+    dev = CudaDevice.make(Options(64, 1, 8), run.local)
+    t0 = time.perf_counter()
+    acc = Accel(scene)
+    dev.preprocess(scene, acc)
+    dev.upload_scene(scene)
+    prep = time.perf_counter() - t0
+    rec = render_frames(run, dev, scene, 64, 8, "tiles", steps=4, warmup=2)
+    rec["workload"] = LABELS["terrain_ggx"]
+    rec["preprocess_s"] = prep
+    dev.close()
+    if run.cpu_legs:
+        rec["cpu_baseline"] = reference_frame_leg(run, scene, 1, 8)
+        rec["e2e_dropin"] = dropin_frame_leg(run, scene, 64, 8)
+    return rec
+
+
+def config5(run: Run):
+    """Sample-partitioned 4K frame of the 30 M-triangle field: 16 samples per pixel per rank (BASELINE's 1024 spp at 8 GPUs
+    is 128 per rank: the same per-rank work x 8, too long for a default run), one NCCL reduce of the 132.7 MB film."""
+    from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
+    scene = scenes.instanced_field()
+    spp = 16 * run.world
+    dev = CudaDevice.make(Options(spp, 1, 8), run.local)
+    t0 = time.perf_counter()
+    acc = Accel(scene)
+    dev.preprocess(scene, acc)
+    dev.upload_scene(scene)
+    prep = time.perf_counter() - t0
+    rec = render_frames(run, dev, scene, spp, 8, "samples", steps=2, warmup=1)
+    rec["scaling"] = "weak"
+    rec["workload"] = LABELS["instanced30m"] + f", {spp} spp = 16 per rank"
+    rec["preprocess_s"] = prep
+    dev.close()
+    return rec
+
+
+def guarded(run: Run, name: str, fn, out: dict):
+    """A failing sub-record must not take the headline down with it — but it must be visible."""
+    try:
+        t0 = time.perf_counter()
+        rec = fn(run)
+        if rec is not None and run.rank == 0:
+            if isinstance(rec, dict) and name == "config3":
+                for k, v in rec.items():
+                    out[f"config3_{k}"] = v
+            else:
+                out[name] = rec
+            out.setdefault("_seconds", {})[name] = round(time.perf_counter() - t0, 1)
+    except Exception as e:  # noqa: BLE001
+        if run.dist:
+            raise  # ranks must not diverge on collectives
+        out[name] = {"error": f"{type(e).__name__}: {e}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="spheres")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of headline,config1,config3,config4,config5 (default: all that apply)")
+    ap.add_argument("--render", action="store_true", help="one path-traced frame record only (--workload, --spp, --depth, --partition)")
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--partition", default="tiles", choices=["tiles", "samples"])
+    args = ap.parse_args()
+    if args.impl != "reference" and not args.render:
+        args.warmup = max(args.warmup, 3)  # timing hygiene for the kernel metric
+
+    scene, label = make_workload(args.workload)
+    if args.impl == "reference":
+        run_reference_arm(args, scene, label)
+        return
+
+    run = Run(args)
+    if args.render:  # a single frame record (tuning / scaling studies)
+        from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
+        dev = CudaDevice.make(Options(args.spp, 1, args.depth), run.local)
+        acc = Accel(scene)
+        dev.preprocess(scene, acc)
+        dev.upload_scene(scene)
+        rec = render_frames(run, dev, scene, args.spp, args.depth, args.partition, args.steps, args.warmup)
+        dev.close()
+        if run.rank == 0:
+            rec.update({"metric": "path-traced samples/s", "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
+                        "data": "synthetic", "config": {"workload": label, "spp": args.spp, "depth": args.depth}})
+            print(json.dumps(rec), flush=True)
+        if run.dist:
+            run.dist.destroy_process_group()
+        return
+
+    only = set(filter(None, args.only.split(",")))
+    want = lambda k: not only or k in only  # noqa: E731
+    line = headline(run, scene, label) if want("headline") or not only else {"metric": "Mrays/s (closest-hit)", "value": None}
+    configs: dict = {}
+    if args.workload == "spheres":
+        if run.world == 1:
+            if want("config1"):
+                guarded(run, "config1_cornell", config1, configs)
+            if want("config3"):
+                guarded(run, "config3", config3, configs)
+        if want("config4"):
+            guarded(run, "config4_frame", config4, configs)
+        if run.world > 1 and want("config5"):
+            guarded(run, "config5_frame", config5, configs)
+    if run.rank == 0:
+        line["configs"] = configs
+        print(json.dumps(line), flush=True)
+    if run.dist:
+        run.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -143,6 +143,11 @@ uint64_t phos_cuda_launch_count(phos_ctx* ctx);
 /* Trace device-resident rays with traversal counters on: total 8-wide nodes box-tested and
  * triangles Moeller-Trumbore-tested over the batch (the N_node / N_tri of the roofline model).  Blocking. */
 int phos_cuda_trace_count(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint64_t* out_nodes, uint64_t* out_tris);
+/* The same launch with the warp-level step statistics of the traversal kernel (bench.py's issue-slot figures):
+ * out[0] nodes box-tested, [1] triangles tested (summed over lanes), [2] warp-level node steps, [3] warp-level triangle
+ * steps, [4] lanes that took part in the node steps, [5] in the triangle steps, [6] loop iterations of all warps,
+ * [7] rays traced (MASKED rays are not).  Blocking. */
+int phos_cuda_trace_profile(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint64_t out[8]);
 /* Bind the calling host thread (and threads it spawns later) to the CPUs local to `device` (sysfs local_cpulist of
  * its PCI function), so page-locked ray arrays allocated afterwards live on the GPU's NUMA node.  One rank per GPU
  * calls this first.  Returns the number of CPUs bound to, 0 if the topology is not exposed (nothing changes). */
@@ -157,8 +162,17 @@ int phos_cuda_flush_l2(phos_ctx* ctx);
 
 /* ---- scene and frame pipeline ------------------------------------------------------------------ */
 /* Upload what tile_renderer_t reads from scene_t while rendering (src/xpu/cpu.cpp:85-99): camera,
- * and for the path tracer meshes, materials, lights.  Pinhole cameras only. */
+ * and for the path tracer meshes, materials, lights (pinhole and thin-lens cameras). */
 int phos_cuda_upload_scene(phos_ctx* ctx, const phos_scene_desc* scene);
+
+/* Reference-compatible normalisation.  The reference normalises camera and shadow-ray directions as
+ * x * _mm256_rcp_ps(sqrt(dot)) (src/math/simd/vector.hpp:94-96,126-133): a ~12-bit reciprocal that leaves shadow rays up
+ * to 3.7e-4 too long, so that a share of them hit the light's own triangle and count as occluded (spt.hpp:116-148) — its
+ * images are 13-40 % darker than exact arithmetic.  on = 1: the library samples the RCPSS of the HOST it runs on into a
+ * table (a function of the leading mantissa bits, verified at sampling time) and the device kernels normalise through it,
+ * so cuda_t tiles match the cpu_t tiles next to them in a shared frame (plugins/blender/session.cpp:85-99).  on = 0
+ * (default): correctly rounded 1 / sqrt.  The traversal is exact in both modes.  Applies to the following renders. */
+int phos_cuda_reference_normalize(phos_ctx* ctx, int on);
 
 /* camera::perspective_kernel_t (src/kernels/cpu/camera.hpp:78-159): primary rays of every pixel of
  * the given tiles for one film jitter (jx, jy) shared by the whole sample, into device ray arrays.
@@ -203,6 +217,26 @@ int phos_cuda_film_read(phos_ctx* ctx, float* rgba, uint32_t x, uint32_t y, uint
  * last sample range has the reference's values.) */
 int phos_cuda_enable_normals(phos_ctx* ctx, int on);
 int phos_cuda_film_read_normals(phos_ctx* ctx, float* xyz, uint32_t x, uint32_t y, uint32_t w, uint32_t h);
+
+/* ---- multi-GPU frames: ONE NCCL reduce of the film per frame (one process per GPU) -------------
+ * The reference shards a frame over the workers of one process through one tile cursor (src/jobs/tiles.hpp:40-47,
+ * src/xpu/cpu.cpp:223-238) into one film_t (src/film.hpp:10-16).  With one process per GPU each rank renders its tiles
+ * (or its sample range) into its own device film and the films meet in
+ *     ncclReduce(film, film, W*H*4, ncclFloat, ncclSum, root)
+ * enqueued on the context's stream behind the frame's kernels (asynchronous; phos_cuda_film_read on the root then sees
+ * the whole frame).  Disjoint tiles make the sum a gather, weighted sample ranges make it the average; alpha is clamped
+ * back to 1.  NCCL is bound at run time (dlopen "libnccl.so.2"), the library has no link-time dependency on it.
+ * N cuda_t devices inside ONE process (xpu_t::discover) need none of this: each hands its own tiles to film_t::add_tile.
+ *   comm_unique_id : ncclGetUniqueId on one rank; the host ships the 128 bytes to the others (any channel);
+ *   comm_init      : ncclCommInitRank for this context's GPU (collective: every rank calls it);
+ *   comm_adopt     : use a communicator the host already owns (an ncclComm_t whose device is this context's) instead;
+ *   film_reduce    : the per-frame reduce (collective). */
+#define PHOS_NCCL_ID_BYTES 128
+int  phos_cuda_comm_unique_id(uint8_t id[PHOS_NCCL_ID_BYTES]);
+int  phos_cuda_comm_init(phos_ctx* ctx, int n_ranks, int rank, const uint8_t id[PHOS_NCCL_ID_BYTES]);
+int  phos_cuda_comm_adopt(phos_ctx* ctx, void* nccl_comm, int n_ranks);
+void phos_cuda_comm_destroy(phos_ctx* ctx);
+int  phos_cuda_film_reduce(phos_ctx* ctx, int root);
 
 #ifdef __cplusplus
 }

@@ -81,7 +81,7 @@ typedef struct phos_scene_desc {
   const float*    normals;         /* xyz per vertex (NormalsPerVertex) or NULL               */
   const uint32_t* face_offset;     /* [num_meshes+1] first face of mesh m in `faces`          */
   const uint32_t* faces;           /* 3 mesh-local vertex indices per face                    */
-  const uint8_t*  mesh_smooth;     /* [num_meshes] 1: every face smooth, 0: every face flat   */
+  const uint8_t*  mesh_smooth;     /* [num_meshes] 1: every face smooth, 0: every face flat, 2: see face_smooth */
   const uint32_t* set_offset;      /* [num_meshes+1] first face set of mesh m                 */
   const uint32_t* set_material;    /* [num_sets] material id of the set                       */
   const uint32_t* set_face_offset; /* [num_sets+1] first entry of set s in `set_faces`        */
@@ -91,6 +91,9 @@ typedef struct phos_scene_desc {
   phos_camera          camera;
   int32_t              environment; /* material id of the environment (PHOS_MAT_BACKGROUND; scene_t::environment(),
                                        src/scene.cpp:64-74,126-128) or -1: what a ray that misses adds to the path */
+  const uint8_t*       face_smooth; /* [total faces] or NULL: the per-face flag of mesh_t::builder_t::add_face(a, b, c, smooth)
+                                       (src/mesh.hpp:46-66, src/mesh.cpp:10-18,202-206), indexed like `faces` / 3; read for
+                                       the faces of meshes whose mesh_smooth is 2 (meshes mixing smooth and flat faces) */
 } phos_scene_desc;
 
 #ifdef __cplusplus

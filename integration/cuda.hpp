@@ -6,7 +6,10 @@
 
 #include "xpu.hpp"
 
+#include <atomic>
+#include <cstddef>
 #include <cstdint>
+#include <exception>
 #include <thread>
 
 struct parsed_options_t;
@@ -16,8 +19,14 @@ struct phos_ctx;
 struct cuda_t : public xpu_t {
   phos_ctx* ctx = nullptr;
   std::thread worker;
+  std::exception_ptr error;  // what the worker threw; rethrown by join()
   uint32_t spp = 16;
   uint64_t seed = 0;
+  uint32_t film_w = 0, film_h = 0;
+  float* pinned = nullptr;  // page-locked landing zone of the film rows of a chunk
+  size_t pinned_bytes = 0;
+  uint32_t tiles_done = 0, claims = 0;  // of the last frame (tests / diagnostics)
+  static std::atomic<int> instances;    // live cuda_t devices: the peers that share a frame's tile queue
 
   ~cuda_t();
 

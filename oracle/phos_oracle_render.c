@@ -25,7 +25,9 @@
  *      with rcp_mode = 0 the shadow-ray and camera-ray directions are normalised exactly.  With
  *      rcp_mode = 1 (x86 only) the same RCPSS instruction is used, which reproduces the reference's
  *      systematic shadow-ray overshoot (a shadow ray whose direction is > 1e-4 / length too long
- *      hits the light's own triangle and is counted as occluded);
+ *      hits the light's own triangle and is counted as occluded), and rays are traced with the
+ *      reference's approximate slab test; rcp_mode = 2 keeps the RCPSS normalisation but traces
+ *      exactly — what the device does under phos_cuda_reference_normalize;
  *   3. a 0-lobe BSDF (pure emitter) is sampled by the reference through uninitialised lobe data
  *      (bsdf.cpp:140-153); here the path simply ends there.
  * All arithmetic keeps the reference's float / double expression shapes; compile with -ffp-contract=off.
@@ -634,7 +636,9 @@ int orc_bsdf_sample(const phos_material* mt, const float* n, const float* wi, fl
 
 /* ---- shading normal: mesh_t::shading_parameters, mesh.cpp:169-206 ------------------------------------------ */
 static v3 shading_normal(const phos_scene_desc* d, uint32_t mesh, uint32_t face3, float u, float v) {
-  if (d->mesh_smooth[mesh] && d->normals) {
+  unsigned smooth = d->mesh_smooth[mesh];
+  if (smooth == 2) smooth = d->face_smooth[(size_t)d->face_offset[mesh] + face3 / 3]; /* mesh_t::details_t::smooth[face], mesh.cpp:10-18 */
+  if (smooth && d->normals) {
     const float w = 1 - u - v;
     const size_t f = 3 * (size_t)d->face_offset[mesh] + face3;
     const size_t ia = d->faces[f] + d->vert_offset[mesh], ib = d->faces[f + 1] + d->vert_offset[mesh],
@@ -717,7 +721,7 @@ void orc_camera_rays_lens(const phos_camera* cam, uint32_t x0, uint32_t y0, uint
 typedef struct { v3 o, w; float d; uint32_t mesh, face; float u, v; uint32_t flags; } ray1;
 static void trace1(const void* nodes, const void* packets, ray1* r, int rcp_mode) {
   orc_rays s = {&r->o.x, &r->o.y, &r->o.z, &r->w.x, &r->w.y, &r->w.z, &r->d, &r->mesh, &r->face, &r->u, &r->v, &r->flags};
-  orc_traverse(nodes, packets, &s, 1, NULL, rcp_mode ? 3 : 1); /* rcp_mode: the reference's own approximate slab test */
+  orc_traverse(nodes, packets, &s, 1, NULL, rcp_mode == 1 ? 3 : 1); /* rcp_mode 1: the reference's own approximate slab test */
 }
 
 /* Path-trace samples [spp_begin, spp_end) of the pixel rectangle [x0,x0+w) x [y0,y0+h) and add

@@ -6,7 +6,9 @@ module; the product package never does.
   Oracle  — oracle/libphos_oracle.so, the plain-C restatement (phos_oracle.c).
   RefLib  — oracle/_ref/libphos_ref.so, the reference's own sources compiled from /root/reference
             (present when `make -C oracle ref` ran in a container that has the reference; the
-            built .so travels to the GPU box, the sources do not).
+            built .so travels to the GPU box, the sources do not).  RefLib(cuda=True) loads
+            oracle/_ref/libphos_ref_cuda.so instead: the same objects plus the drop-in GPU device
+            (integration/cuda.cpp, integration/xpu_discover.patch) linked against libphos_cuda.so.
 """
 from __future__ import annotations
 
@@ -21,7 +23,8 @@ from phosphorus_mk2_b200.scene import PhosSceneDesc, Scene
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libphos_oracle.so")
-REF_SO = os.path.join(HERE, "_ref", "libphos_ref.so")
+REF_SO = os.path.join(HERE, "_ref", "libphos_ref.so")            # the reference alone: maps no product code
+REF_CUDA_SO = os.path.join(HERE, "_ref", "libphos_ref_cuda.so")  # + the drop-in cuda_t (integration/) -> libphos_cuda.so
 NODE_BYTES, PACKET_BYTES = 288, 384
 
 
@@ -83,7 +86,7 @@ class Oracle:
 
 
     def render(self, scene: Scene, nodes: np.ndarray, packets: np.ndarray, spp: int, pps: int = 1, depth: int = 9,
-               seed: int = 0, region=None, spp_range=None, rcp_mode: bool = False, film: np.ndarray | None = None,
+               seed: int = 0, region=None, spp_range=None, rcp_mode: bool | int = False, film: np.ndarray | None = None,
                normals: np.ndarray | None = None):
         """Scalar path tracer over a pixel rectangle (default: whole film); returns the RGBA film.  `normals`
         (H, W, 3 float32) receives the NORMALS channel (cpu.cpp:194-196) when given."""
@@ -95,7 +98,7 @@ class Oracle:
         x0, y0, w, hh = region if region is not None else (0, 0, cam.film_width, cam.film_height)
         s0, s1 = spp_range if spp_range is not None else (0, spp)
         self.lib.orc_render(h, nodes.ctypes.data, packets.ctypes.data, x0, y0, w, hh, s0, s1, spp, pps, depth, seed,
-                            1 if rcp_mode else 0, film.ctypes.data, normals.ctypes.data if normals is not None else None)
+                            int(rcp_mode), film.ctypes.data, normals.ctypes.data if normals is not None else None)
         self.lib.orc_scene_destroy(h)
         return film
 
@@ -179,6 +182,22 @@ class RefScene:
             raise RuntimeError("device raised (see stderr)")
         return img, secs
 
+    def render_devices(self, spp: int, pps: int = 1, depth: int = 9, n_cuda: int = 1, with_cpu: bool = False,
+                       cpu_single_threaded: bool = False):
+        """One frame on several devices sharing frame.tiles (session.cpp:85-99): n_cuda cuda_t (+ the reference's cpu_t).
+        Returns (image, seconds, tiles rendered per cuda device)."""
+        cam = self._scene.camera
+        img = np.zeros((cam.film_height, cam.film_width, 4), np.float32)
+        per = (C.c_int * (n_cuda + 1))()
+        secs = self.lib.ref_render_devices(self.h, spp, pps, depth, n_cuda, 1 if with_cpu else 0, 1 if cpu_single_threaded else 0,
+                                           img.ctypes.data, per)
+        if secs < 0:
+            raise RuntimeError("a device raised (see stderr)")
+        return img, secs, [int(per[i]) for i in range(n_cuda)]
+
+    def cuda_join_raises(self) -> int:
+        return int(self.lib.ref_cuda_join_raises(self.h))
+
     def render_cuda(self, spp: int, pps: int = 1, depth: int = 9):
         """The same frame through the drop-in GPU device: the reference's host code (scene_t, tiles_t,
         sampler, film_t) driving cuda_t::preprocess/start/join (integration/cuda.cpp -> libphos_cuda.so)."""
@@ -226,11 +245,12 @@ class RefScene:
 
 class RefLib:
     @staticmethod
-    def available() -> bool:
-        return os.path.exists(REF_SO)
+    def available(cuda: bool = False) -> bool:
+        return os.path.exists(REF_CUDA_SO if cuda else REF_SO)
 
-    def __init__(self):
-        self.lib = L = C.CDLL(REF_SO)
+    def __init__(self, cuda: bool = False):
+        self.cuda = cuda
+        self.lib = L = C.CDLL(REF_CUDA_SO if cuda else REF_SO)
         L.ref_scene_create.restype = C.c_void_p
         L.ref_scene_create.argtypes = [C.POINTER(PhosSceneDesc)]
         L.ref_scene_destroy.argtypes = [C.c_void_p]
@@ -256,6 +276,14 @@ class RefLib:
         L.ref_bsdf_sample.restype = C.c_int
         L.ref_camera_rays.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_float, C.c_float] + [C.c_void_p] * 8
         L.ref_cuda_device_count.restype = C.c_int
+        if cuda:
+            L.ref_discover.argtypes = [C.c_int, C.POINTER(C.c_int)]
+            L.ref_discover.restype = C.c_int
+            L.ref_render_devices.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.POINTER(C.c_int)]
+            L.ref_render_devices.restype = C.c_double
+            L.ref_cuda_join_raises.argtypes = [C.c_void_p]
+            L.ref_cuda_join_raises.restype = C.c_int
         L.ref_hardware_concurrency.restype = C.c_uint32
         L.ref_sizeof_node.restype = C.c_uint32
         L.ref_sizeof_packet.restype = C.c_uint32
@@ -263,6 +291,12 @@ class RefLib:
 
     def scene(self, scene: Scene) -> RefScene:
         return RefScene(self.lib, scene)
+
+    def discover(self, host_only: bool = False):
+        """(devices, of which GPUs) xpu_t::discover returns (src/xpu.cpp:7-9 + integration/xpu_discover.patch)."""
+        n = C.c_int(0)
+        total = self.lib.ref_discover(1 if host_only else 0, C.byref(n))
+        return int(total), int(n.value)
 
     def hardware_concurrency(self) -> int:
         return int(self.lib.ref_hardware_concurrency())

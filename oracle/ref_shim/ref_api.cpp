@@ -22,6 +22,7 @@
 #include "state.hpp"
 #include "xpu/cpu.hpp"
 #include "xpu/cuda.hpp"
+#include "xpu.hpp"
 // after scene.hpp: the kernel header uses camera_t without including entities/camera.hpp itself
 #include "kernels/cpu/camera.hpp"
 
@@ -75,8 +76,8 @@ void fill_scene(scene_t& scene, const phos_scene_desc* d) {
           b->add_normal(Imath::V3f(d->normals[3 * v], d->normals[3 * v + 1], d->normals[3 * v + 2]));
         }
       }
-      const bool smooth = d->mesh_smooth[m] != 0;
       for (uint32_t f = d->face_offset[m]; f < d->face_offset[m + 1]; ++f) {
+        const bool smooth = d->mesh_smooth[m] == 2 ? d->face_smooth[f] != 0 : d->mesh_smooth[m] != 0;
         b->add_face(d->faces[3 * f], d->faces[3 * f + 1], d->faces[3 * f + 2], smooth);
       }
       for (uint32_t s = d->set_offset[m]; s < d->set_offset[m + 1]; ++s) {
@@ -293,7 +294,12 @@ double ref_render_aov(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int s
 
   xpu_t* device = nullptr;
   try {
+#ifdef REF_WITH_CUDA
     device = use_cuda ? static_cast<xpu_t*>(cuda_t::make(options, 0)) : static_cast<xpu_t*>(cpu_t::make(options));
+#else
+    if (use_cuda) throw std::runtime_error("this build holds the reference alone (load libphos_ref_cuda.so for cuda_t)");
+    device = cpu_t::make(options);
+#endif
     device->preprocess(s->scene);
   } catch (const std::exception& e) {
     std::cerr << "ref_render_on: " << e.what() << std::endl;
@@ -322,7 +328,115 @@ double ref_render_aov(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int s
   return dt;
 }
 
+#ifdef REF_WITH_CUDA
 int ref_cuda_device_count(void) { return cuda_t::device_count(); }
+
+// How many devices xpu_t::discover (src/xpu.cpp:7-9 + integration/xpu_discover.patch) returns, and how many are GPUs.
+int ref_discover(int host_only, int* out_cuda) {
+  parsed_options_t options;
+  options.host_only = host_only != 0;
+  options.samples_per_pixel = 1;
+  options.paths_per_sample = 1;
+  const int before = cuda_t::instances.load();
+  std::vector<xpu_t*> devices = xpu_t::discover(options);
+  const int n_cuda = cuda_t::instances.load() - before;  // (built without RTTI: count the live cuda_t devices)
+  for (xpu_t* d : devices) delete d;
+  if (out_cuda) *out_cuda = n_cuda;
+  return (int)devices.size();
+}
+
+// One frame on SEVERAL devices that share frame.tiles, exactly the loops of session_t::details_t::render / prepare_devices
+// (plugins/blender/session.cpp:85-99,121-132): n_cuda cuda_t devices (GPU i % device_count) and, with_cpu, the reference's
+// own cpu_t next to them.  tiles_per_device[i] receives the tiles cuda device i rendered (the rest went to cpu_t).
+// Returns seconds around start..join, or -1 if a device raised (message on stderr).
+double ref_render_devices(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int n_cuda, int with_cpu, int cpu_single_threaded,
+                          float* rgba, int* tiles_per_device) {
+  auto* s = static_cast<ref_scene*>(h);
+  parsed_options_t options;
+  options.samples_per_pixel = spp;
+  options.paths_per_sample = pps;
+  options.path_depth = depth;
+  options.single_threaded = cpu_single_threaded != 0;
+  options.host_only = false;
+  const uint32_t W = s->scene.camera.film.width, H = s->scene.camera.film.height;
+  render_buffer_t::descriptor_t format;
+  format.request(render_buffer_t::PRIMARY, 4);
+  std::vector<xpu_t*> devices;
+  std::vector<cuda_t*> gpus;
+  double dt = -1.0;
+  try {
+    const int n_gpu = cuda_t::device_count();
+    for (int i = 0; i < n_cuda; ++i) {
+      gpus.push_back(cuda_t::make(options, n_gpu > 0 ? i % n_gpu : 0));
+      devices.push_back(gpus.back());
+    }
+    if (with_cpu) devices.push_back(cpu_t::make(options));
+    for (xpu_t* d : devices) d->preprocess(s->scene);
+    job::tiles_t* tiles = job::tiles_t::make(W, H, 32, format);
+    memory_film_t film;
+    film.rgba = rgba;
+    film.width = W;
+    film.height = H;
+    sampler_t* sampler = new sampler_t(options);
+    frame_state_t state(sampler, tiles, &film);
+    sampler->preprocess(s->scene);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (xpu_t* d : devices) d->start(s->scene, state);
+    for (xpu_t* d : devices) d->join();
+    dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t i = 0; tiles_per_device && i < gpus.size(); ++i) tiles_per_device[i] = (int)gpus[i]->tiles_done;
+    delete tiles;
+  } catch (const std::exception& e) {
+    std::cerr << "ref_render_devices: " << e.what() << std::endl;
+    dt = -1.0;
+  }
+  for (xpu_t* d : devices) delete d;
+  return dt;
+}
+
+// cuda_t::join must surface what the worker threw (a throw out of a std::thread would terminate the process): start a
+// frame whose tile queue holds a tile outside the film.  Returns 1 if join() raised, 0 if it did not.
+int ref_cuda_join_raises(void* h) {
+  auto* s = static_cast<ref_scene*>(h);
+  parsed_options_t options;
+  options.samples_per_pixel = 1;
+  options.paths_per_sample = 1;
+  options.path_depth = 2;
+  options.host_only = false;
+  const uint32_t W = s->scene.camera.film.width, H = s->scene.camera.film.height;
+  render_buffer_t::descriptor_t format;
+  format.request(render_buffer_t::PRIMARY, 4);
+  cuda_t* device = cuda_t::make(options, 0);
+  int raised = 0;
+  std::vector<float> rgba((size_t)W * H * 4);
+  try {
+    device->preprocess(s->scene);
+    job::tiles_t* tiles = job::tiles_t::make(W, H, 32, format);
+    tiles->tiles[0].x = W;  // outside the film: phos_cuda_render rejects it inside the worker
+    memory_film_t film;
+    film.rgba = rgba.data();
+    film.width = W;
+    film.height = H;
+    sampler_t* sampler = new sampler_t(options);
+    frame_state_t state(sampler, tiles, &film);
+    sampler->preprocess(s->scene);
+    device->start(s->scene, state);
+    try {
+      device->join();
+    } catch (const std::exception&) {
+      raised = 1;
+    }
+    delete tiles;
+  } catch (const std::exception& e) {
+    std::cerr << "ref_cuda_join_raises: " << e.what() << std::endl;
+    raised = -1;
+  }
+  delete device;
+  return raised;
+}
+#else
+int ref_cuda_device_count(void) { return 0; }
+#endif
 
 uint32_t ref_hardware_concurrency(void) { return std::thread::hardware_concurrency(); }
 

@@ -11,7 +11,8 @@
 // computes is never read), its constants named pi_o_4 / pi_o_2 hold 4/pi and 2/pi, and simd::select(m, l, r)
 // is m ? r : l (float8.hpp:103-105) — the CPU restatement the tests compare against is pinned bit for
 // bit to the compiled reference kernel (tests/).  Differences to the reference, as for
-// every normalisation on the device: IEEE 1 / sqrt instead of the 12-bit RCPPS; CUDA sinf / cosf.
+// every normalisation on the device: IEEE 1 / sqrt instead of the 12-bit RCPPS (unless the reference-
+// compatible mode samples the host's RCPPS into a table, below); CUDA sinf / cosf.
 // Every operation is an explicit round-to-nearest intrinsic: the result does not depend on -fmad.
 #pragma once
 #include <cuda_runtime.h>
@@ -21,12 +22,31 @@
 namespace phos {
 
 struct DevCamera {
+  // reference-compatible normalisation (phos_cuda_reference_normalize): the host's RCPSS as a table over the leading
+  // mantissa bits (rcp_table.cpp); null = exact 1 / sqrt
+  const float* rcp_tab;
+  uint32_t rcp_shift;  // 23 - bits
   float m[16];  // to_world, row-vector convention
   float zoom;   // 1.12 * tan(fov / 2)
   float stepx, stepy, ratio;
   float focal_distance, aperture_radius;
   uint32_t width, height;
 };
+
+// _mm256_rcp_ps(x) of the host for a positive normal x: the table entry of the leading mantissa bits, exponent negated
+__device__ __forceinline__ float reference_rcp(const float* __restrict__ tab, uint32_t shift, float x) {
+  const uint32_t b = __float_as_uint(x);
+  const uint32_t e = (b >> 23) & 0xffu;
+  if (e == 0u || e == 255u || (b >> 31)) return __fdiv_rn(1.0f, x);  // zero / denormal / inf / nan / negative: not a length
+  return __uint_as_float(__float_as_uint(__ldg(tab + ((b & 0x7fffffu) >> shift))) - ((e - 127u) << 23));
+}
+
+// 1 / length the way vector3_t<8>::normalize does it (src/math/simd/vector.hpp:126-133): rcp(sqrt(l)) — exact division
+// unless the reference-compatible mode is on
+__device__ __forceinline__ float inv_length(const DevCamera& cam, float l) {
+  const float s = __fsqrt_rn(l);
+  return cam.rcp_tab ? reference_rcp(cam.rcp_tab, cam.rcp_shift, s) : __fdiv_rn(1.0f, s);
+}
 
 __device__ __forceinline__ void camera_ray(const DevCamera& cam, uint32_t px, uint32_t py, float jx, float jy, float lu,
                                            float lv, float* o, float* w) {
@@ -37,7 +57,7 @@ __device__ __forceinline__ void camera_ray(const DevCamera& cam, uint32_t px, ui
   float dy = __fmul_rn(__fadd_rn(ndcy, __fmul_rn(jy, cam.stepy)), cam.zoom);
   float dz = -1.0f;
   float l = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
-  float ool = __fdiv_rn(1.0f, __fsqrt_rn(l));
+  float ool = inv_length(cam, l);
   dx = __fmul_rn(dx, ool);
   dy = __fmul_rn(dy, ool);
   dz = __fmul_rn(dz, ool);
@@ -56,7 +76,7 @@ __device__ __forceinline__ void camera_ray(const DevCamera& cam, uint32_t px, ui
     dy = __fsub_rn(__fmul_rn(dy, ft), ly);
     dz = __fsub_rn(__fmul_rn(dz, ft), 0.0f);
     l = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
-    ool = __fdiv_rn(1.0f, __fsqrt_rn(l));
+    ool = inv_length(cam, l);
     dx = __fmul_rn(dx, ool);
     dy = __fmul_rn(dy, ool);
     dz = __fmul_rn(dz, ool);

@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/phos_cuda.h"
 
@@ -47,6 +48,12 @@ struct phos_ctx {
   phos::PipeLane pipe[phos::kPipe];
   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr, s_in2 = nullptr;
   phos::RenderState* render = nullptr;
+  float* d_rcp_table = nullptr;  // the host's RCPSS sampled over the leading mantissa bits (phos_cuda_reference_normalize)
+  int rcp_bits = 11;
+  bool reference_rcp = false;
+  void* nccl_comm = nullptr;  // the communicator of phos_cuda_film_reduce (comm.cu)
+  bool nccl_owned = false;
+  int nccl_ranks = 0;
   void* d_flush = nullptr;  // L2 flush scratch (bench hygiene)
   int flush_value = 0;
 };
@@ -59,4 +66,6 @@ void free_rays(phos_rays& r);
 int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t stream, unsigned long long* cursor,
                  bool count, const uint32_t* n_ptr = nullptr);
 void phos_render_release(phos_ctx* ctx);  // render.cu
+void comm_release(phos_ctx* ctx);         // comm.cu
+bool sample_host_rcp(std::vector<float>& table, int& bits);  // rcp_table.cpp
 }  // namespace phos

@@ -94,7 +94,8 @@ struct DevScene {
   const uint32_t* faces;
   const uint32_t* vert_offset;
   const uint32_t* face_offset;
-  const uint8_t* mesh_smooth;
+  const uint8_t* mesh_smooth;  // 0 flat, 1 smooth, 2 mixed: per face in face_smooth
+  const uint8_t* face_smooth;  // per face (scene-wide face index); null when no mesh mixes smooth and flat faces
   const DevMaterial* mats;
   int32_t environment;  // material id of the environment or -1 (scene_t::environment())
   uint32_t nlights;
@@ -112,7 +113,9 @@ __device__ __forceinline__ v3 scene_vert(const DevScene& S, uint32_t mesh, uint3
 // mesh_t::shading_parameters, mesh.cpp:169-206: interpolated vertex normal (w on a, u on b, v on c)
 // for smooth meshes, geometric normal (v1 - v0) x (v2 - v0) otherwise; never face-forwarded (:209-215)
 __device__ __forceinline__ v3 shading_normal(const DevScene& S, uint32_t mesh, uint32_t face3, float u, float v) {
-  if (__ldg(S.mesh_smooth + mesh) && S.normals) {
+  uint32_t smooth = __ldg(S.mesh_smooth + mesh);
+  if (smooth == 2u) smooth = __ldg(S.face_smooth + (size_t)__ldg(S.face_offset + mesh) + face3 / 3u);  // the face's own flag
+  if (smooth && S.normals) {
     const float w = 1 - u - v;
     const size_t f = 3 * (size_t)__ldg(S.face_offset + mesh) + face3;
     const size_t vo = __ldg(S.vert_offset + mesh);

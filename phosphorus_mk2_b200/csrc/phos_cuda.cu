@@ -134,11 +134,33 @@ int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t s
   // (PHOS_TRACE_DEEP=1 forces the deep instantiation: tests/test_gpu_trace.py)
   // (a ray holds at most one pending sibling group per level below the root: max_depth entries)
   const bool deep = ctx->stats.max_depth > (uint32_t)kSmemStack || std::getenv("PHOS_TRACE_DEEP") != nullptr;
+#ifdef PHOS_TAIL_PROBE
+  // tuning probe: per-warp start / stream-dry / end times of this launch, appended to $PHOS_TAIL_PROBE_FILE
+  static unsigned long long* d_probe = nullptr;
+  const size_t probe_words = 5ull * (size_t)grid * kTraceWarps;
+  const char* probe_file = std::getenv("PHOS_TAIL_PROBE_FILE");
+  if (!d_probe) cudaMalloc(&d_probe, 5ull * 8 * 148 * 16 * kTraceWarps);
+  a.probe = probe_file ? d_probe : nullptr;
+  if (probe_file) cudaMemsetAsync(d_probe, 0, probe_words * 8, stream);
+#endif
   if (count) trace_kernel<true, true><<<grid, kTraceBlock, 0, stream>>>(a);
   else if (deep) trace_kernel<false, true><<<grid, kTraceBlock, 0, stream>>>(a);
   else trace_kernel<false, false><<<grid, kTraceBlock, 0, stream>>>(a);
   ctx->launches++;
   if (!cuda_ok(ctx, cudaGetLastError(), "trace_kernel launch")) return PHOS_ERR_CUDA;
+#ifdef PHOS_TAIL_PROBE
+  if (probe_file) {
+    std::vector<unsigned long long> h(probe_words + 2);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data() + 2, d_probe, probe_words * 8, cudaMemcpyDeviceToHost);
+    h[0] = probe_words / 5;
+    h[1] = n;
+    if (FILE* f = fopen(probe_file, "ab")) {
+      fwrite(h.data(), 8, h.size(), f);
+      fclose(f);
+    }
+  }
+#endif
   return PHOS_OK;
 }
 
@@ -213,11 +235,13 @@ void phos_cuda_destroy(phos_ctx* ctx) {
   }
   for (cudaStream_t st : {ctx->s_in, ctx->s_cmp, ctx->s_out, ctx->s_in2})
     if (st) cudaStreamDestroy(st);
+  comm_release(ctx);
   phos_render_release(ctx);
   if (ctx->d_nodes) cudaFree(ctx->d_nodes);
   if (ctx->d_tris) cudaFree(ctx->d_tris);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_flush) cudaFree(ctx->d_flush);
+  if (ctx->d_rcp_table) cudaFree(ctx->d_rcp_table);
   if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -281,7 +305,7 @@ int phos_cuda_trace_count(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint
   if (!ctx || !rays) return PHOS_ERR_INVALID;
   if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "trace before upload_accel");
   cudaSetDevice(ctx->device);
-  if (!cuda_ok(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream), "memset")) return PHOS_ERR_CUDA;
+  if (!cuda_ok(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream), "memset")) return PHOS_ERR_CUDA;
   const int rc = launch_trace(ctx, *rays, n, ctx->stream, ctx->d_counters + 8, true);
   if (rc) return rc;
   unsigned long long c[2];
@@ -290,6 +314,21 @@ int phos_cuda_trace_count(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint
     return PHOS_ERR_CUDA;
   if (out_nodes) *out_nodes = c[0];
   if (out_tris) *out_tris = c[1];
+  return PHOS_OK;
+}
+
+int phos_cuda_trace_profile(phos_ctx* ctx, const phos_rays* rays, uint64_t n, uint64_t out[8]) {
+  if (!ctx || !rays || !out) return PHOS_ERR_INVALID;
+  if (!ctx->has_accel) return fail(ctx, PHOS_ERR_INVALID, "trace before upload_accel");
+  cudaSetDevice(ctx->device);
+  if (!cuda_ok(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream), "memset")) return PHOS_ERR_CUDA;
+  const int rc = launch_trace(ctx, *rays, n, ctx->stream, ctx->d_counters + 8, true);
+  if (rc) return rc;
+  unsigned long long c[8];
+  if (!cuda_ok(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream), "read counters") ||
+      !cuda_ok(ctx, cudaStreamSynchronize(ctx->stream), "sync"))
+    return PHOS_ERR_CUDA;
+  for (int k = 0; k < 8; ++k) out[k] = c[k];
   return PHOS_OK;
 }
 

@@ -54,6 +54,8 @@ __global__ void camera_rays_kernel(const DevCamera cam, const phos_tile* __restr
 
 DevCamera make_camera(const phos_camera& c) {
   DevCamera d;
+  d.rcp_tab = nullptr;
+  d.rcp_shift = 0;
   memcpy(d.m, c.to_world, sizeof(d.m));
   d.zoom = 1.12f * std::tan(c.fov * 0.5f);
   d.stepx = 1.0f / (float)c.film_width;
@@ -80,7 +82,31 @@ int phos_cuda_upload_scene(phos_ctx* ctx, const phos_scene_desc* scene) {
   phos_render_release(ctx);
   ctx->render = new RenderState();
   ctx->render->camera = make_camera(scene->camera);
+  ctx->render->camera.rcp_tab = ctx->reference_rcp ? ctx->d_rcp_table : nullptr;
+  ctx->render->camera.rcp_shift = 23u - (uint32_t)ctx->rcp_bits;
   return ctx->render->upload(ctx, scene);
+}
+
+int phos_cuda_reference_normalize(phos_ctx* ctx, int on) {
+  if (!ctx) return PHOS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (on && !ctx->d_rcp_table) {
+    std::vector<float> table;
+    int bits = 0;
+    if (!sample_host_rcp(table, bits))
+      return fail(ctx, PHOS_ERR_INVALID, "reference_normalize: this host has no RCPSS that fits the leading-bits model");
+    if (!cuda_ok(ctx, cudaMalloc(&ctx->d_rcp_table, table.size() * sizeof(float)), "cudaMalloc(rcp table)") ||
+        !cuda_ok(ctx, cudaMemcpy(ctx->d_rcp_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice), "upload rcp table"))
+      return PHOS_ERR_CUDA;
+    ctx->rcp_bits = bits;
+  }
+  ctx->reference_rcp = on != 0;
+  if (ctx->render) {  // frames already uploaded switch too (the stream is drained first: kernels hold the camera by value)
+    cudaStreamSynchronize(ctx->stream);
+    ctx->render->camera.rcp_tab = ctx->reference_rcp ? ctx->d_rcp_table : nullptr;
+    ctx->render->camera.rcp_shift = 23u - (uint32_t)ctx->rcp_bits;
+  }
+  return PHOS_OK;
 }
 
 int phos_cuda_camera_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, float jx, float jy,
@@ -173,6 +199,12 @@ int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
   const size_t nv = d->vert_offset[nm], nf = d->face_offset[nm];
   for (uint32_t m = 0; m < nm; ++m)
     if (d->mesh_smooth[m] && !d->normals) return fail(ctx, PHOS_ERR_INVALID, "smooth mesh without vertex normals");
+  bool mixed = false;
+  for (uint32_t m = 0; m < nm; ++m) {
+    if (d->mesh_smooth[m] > 2) return fail(ctx, PHOS_ERR_INVALID, "mesh_smooth must be 0, 1 or 2");
+    mixed = mixed || d->mesh_smooth[m] == 2;
+  }
+  if (mixed && !d->face_smooth) return fail(ctx, PHOS_ERR_INVALID, "mesh_smooth = 2 without face_smooth");
   const uint32_t nsets = d->set_offset[nm];
   for (uint32_t s = 0; s < nsets; ++s)
     if (d->set_material[s] >= d->num_materials) return fail(ctx, PHOS_ERR_INVALID, "face set with an unknown material");
@@ -278,6 +310,8 @@ int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
             to_device(ctx, *this, light_tri_mesh.data(), light_tri_mesh.size(), &scene.light_tri_mesh) &&
             to_device(ctx, *this, light_tri_face.data(), light_tri_face.size(), &scene.light_tri_face);
   scene.mats = dm;
+  scene.face_smooth = nullptr;
+  if (ok && mixed) ok = to_device(ctx, *this, d->face_smooth, nf, &scene.face_smooth);
   scene.normals = nullptr;
   if (ok && d->normals) ok = to_device(ctx, *this, d->normals, 3 * nv, &scene.normals);
   if (!ok) return PHOS_ERR_CUDA;

@@ -46,19 +46,48 @@ namespace phos {
 #ifndef PHOS_TRI_PAIR
 #define PHOS_TRI_PAIR 1
 #endif
+// The end of a launch (profiles/r02_tail_probe.md).  Guided claims: once fewer than PHOS_TAIL_DIV full chunks per warp
+// are unclaimed, a claim takes its share of what is left (>= PHOS_TAIL_MIN rays, a multiple of 4 so that chunk starts
+// stay 16-byte aligned for the bulk copies) — no warp sits on two staged chunks while others run dry.  0 = fixed claims.
+#ifndef PHOS_TAIL_DIV
+#define PHOS_TAIL_DIV 2
+#endif
+#ifndef PHOS_TAIL_MIN
+#define PHOS_TAIL_MIN 4
+#endif
+// Work sharing: once a warp has nothing left to refill from, lanes without a ray take pending sibling groups off the
+// traversal stacks of the lanes that still have one (the same ray, a disjoint part of the tree) and hand their hit
+// back when done — the longest ray of a warp no longer runs on one lane while 31 wait.  0 = off.
+#ifndef PHOS_TAIL_SHARE
+#define PHOS_TAIL_SHARE 1
+#endif
 constexpr int kChunk = PHOS_CHUNK;           // rays per claimed chunk
 constexpr int kRefillMin = PHOS_REFILL_MIN;  // idle lanes that trigger a refill
 constexpr int kTraceWarps = kTraceBlock / 32;
+constexpr uint32_t kHelper = 0x80000000u;    // Ray::flags of a lane that helps another lane's ray (never written out)
 
 struct TraceArgs {
   phos_rays rays;  // device pointers
   unsigned long long n;
   DevAccel accel;
   unsigned long long* cursor;    // chunk counter (zeroed before launch)
-  unsigned long long* counters;  // [2]: nodes visited, triangles tested (kCount only)
+  // kCount only, [8]: nodes box-tested, triangles tested (per lane); warp-level node steps, triangle steps; lanes that took
+  // part in the node steps, in the triangle steps; loop iterations; rays traced
+  unsigned long long* counters;
   int tma_ok;                    // all eight input arrays are 16-byte aligned
   const uint32_t* n_ptr;         // when set, the stream length is read from HBM (wavefront queues)
+#ifdef PHOS_TAIL_PROBE
+  unsigned long long* probe;     // tuning probe (tools/tail_probe.py): 5 words per warp, see the end of trace_kernel
+#endif
 };
+
+#ifdef PHOS_TAIL_PROBE
+__device__ __forceinline__ unsigned long long probe_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -93,6 +122,10 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   __shared__ alignas(8) unsigned long long s_bar[kTraceWarps][2];
 
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#ifdef PHOS_TAIL_PROBE
+  const unsigned long long pr_start = probe_now();
+  unsigned long long pr_dry = 0, pr_iters = 0, pr_lanes = 0;
+#endif
   const unsigned long long N = P.n_ptr ? (unsigned long long)*P.n_ptr : P.n;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint32_t(*stage)[8][kChunk] = s_stage[warp];
@@ -116,32 +149,45 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   uint32_t cur_cnt = 0, taken = 0, nxt_cnt = 0;
   bool nxt_tma = false, exhausted = false;
 
-  const unsigned long long n_warps = (unsigned long long)gridDim.x * kTraceWarps;
   bool first_claim = true;
   auto claim = [&](int buf) {  // claim the next chunk of the stream and start staging it into `buf`
     nxt_cnt = 0;
     if (exhausted) return;
-    unsigned long long c = 0;
+    unsigned long long base = 0;
+    uint32_t want = kChunk;
     if (first_claim) {  // chunk = global warp index: 4144 warps do not queue up on one atomic at the start
-      c = (unsigned long long)blockIdx.x * kTraceWarps + warp;
+      base = ((unsigned long long)blockIdx.x * kTraceWarps + warp) * kChunk;
       first_claim = false;
     } else {
-      if (lane == 0) c = atomicAdd(P.cursor, 1ull);
-      c = __shfl_sync(0xffffffffu, c, 0) + n_warps;
+      // (recomputed per claim rather than held in registers over the traversal loop)
+      const unsigned long long static_rays = (unsigned long long)gridDim.x * (kTraceWarps * kChunk);  // every warp's first chunk is assigned
+      if (lane == 0) {
+        if (PHOS_TAIL_DIV) {
+          const float tail_share = __fdividef(1.0f, (float)((PHOS_TAIL_DIV ? PHOS_TAIL_DIV : 1) * kTraceWarps * gridDim.x));  // what is unclaimed right now (a plain read just before the atomic), shared out over the warps
+          const unsigned long long pos = *(volatile unsigned long long*)P.cursor + static_rays;
+          const float left = pos < N ? (float)(uint32_t)(N - pos) : 0.0f;
+          want = min((uint32_t)kChunk, max((uint32_t)PHOS_TAIL_MIN, (uint32_t)(left * tail_share) & ~3u));
+        }
+        base = atomicAdd(P.cursor, (unsigned long long)want);  // the cursor counts rays past the static chunks
+      }
+      base = __shfl_sync(0xffffffffu, base, 0) + static_rays;
+      if (PHOS_TAIL_DIV) want = __shfl_sync(0xffffffffu, want, 0);
     }
-    const unsigned long long base = c * kChunk;
     if (base >= N) {
       exhausted = true;
+#ifdef PHOS_TAIL_PROBE
+      pr_dry = probe_now();
+#endif
       return;
     }
     nxt_base = (uint32_t)base;
-    nxt_cnt = (uint32_t)min((unsigned long long)kChunk, N - base);
-    nxt_tma = P.tma_ok && nxt_cnt == kChunk;
+    nxt_cnt = (uint32_t)min((unsigned long long)want, N - base);
+    nxt_tma = P.tma_ok && nxt_cnt == want;  // whole claims are multiples of 4 rays: 16-byte sizes and addresses
     if (nxt_tma) {
       if (lane == 0) {
-        mbar_expect_tx(&bar[buf], 8u * kChunk * 4u);
+        mbar_expect_tx(&bar[buf], 8u * nxt_cnt * 4u);
 #pragma unroll
-        for (int a = 0; a < 8; ++a) bulk_g2s(stage[buf][a], src[a] + base, kChunk * 4u, &bar[buf]);
+        for (int a = 0; a < 8; ++a) bulk_g2s(stage[buf][a], src[a] + base, nxt_cnt * 4u, &bar[buf]);
       }
     } else {
 #pragma unroll
@@ -194,67 +240,35 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   // in the open leaf (bits 8-11); tptr = next triangle; lcounts / lbase = the node's leaf table
   uint32_t lt = 0, tptr = 0, lcounts = 0, lbase = 0;
   uint32_t n_nodes = 0, n_tris = 0;
+  uint32_t w_node = 0, w_tri = 0, l_node = 0, l_tri = 0, w_iter = 0, n_rays = 0;  // kCount: warp-level step statistics
 
-  for (;;) {
-    // 1. what every lane wants to do next (two ballots drive everything else)
-    const bool tri_work = has_ray && lt != 0u;
-    const bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
-    const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
-    const unsigned nl = __ballot_sync(0xffffffffu, node_work);
-    // 2. enough lanes without work (finished rays or empty lanes): retire and refill from the chunk
-    const int n_tri = __popc(tl), n_node = __popc(nl);  // disjoint sets: the rest of the warp is without work
-    if (32 - n_tri - n_node >= kRefillMin) {
-      if (has_ray && !tri_work && !node_work) {
-        if (r.tri != kNoTri) {  // something was accepted (accept_hit marks shadow rays too)
-          P.rays.d[ridx] = r.d;
-          P.rays.flags[ridx] = r.flags;
-          if (!(r.flags & PHOS_SHADOW)) {
-            const uint4 ids = __ldg(P.accel.tris + 3ull * r.tri + 2);  // changed and not SHADOW: a triangle is held
-            P.rays.mesh[ridx] = ids.y;
-            P.rays.face[ridx] = ids.z;
-            P.rays.u[ridx] = r.u;
-            P.rays.v[ridx] = r.v;
-          }
-        }
-        has_ray = false;
+  // hit record of a finished ray -> the stream
+  auto retire = [&]() {
+    if (r.tri != kNoTri) {  // something was accepted (accept_hit marks shadow rays too)
+      P.rays.d[ridx] = r.d;
+      P.rays.flags[ridx] = r.flags;
+      if (!(r.flags & PHOS_SHADOW)) {
+        const uint4 ids = __ldg(P.accel.tris + 3ull * r.tri + 2);  // changed and not SHADOW: a triangle is held
+        P.rays.mesh[ridx] = ids.y;
+        P.rays.face[ridx] = ids.z;
+        P.rays.u[ridx] = r.u;
+        P.rays.v[ridx] = r.v;
       }
-      if (taken < cur_cnt || nxt_cnt != 0) {
-        unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
-        while (idle) {
-          if (taken == cur_cnt && !advance()) break;
-          const uint32_t rank = __popc(idle & lt_mask);
-          const uint32_t take = min((uint32_t)__popc(idle), cur_cnt - taken);
-          if (!has_ray && rank < take) {
-            const uint32_t k = taken + rank;
-            const uint32_t fl = stage[cur_buf][7][k];
-            if (!(fl & PHOS_MASKED)) {  // MASKED rays are consumed without being traced
-              r.ox = __uint_as_float(stage[cur_buf][0][k]);
-              r.oy = __uint_as_float(stage[cur_buf][1][k]);
-              r.oz = __uint_as_float(stage[cur_buf][2][k]);
-              r.wx = __uint_as_float(stage[cur_buf][3][k]);
-              r.wy = __uint_as_float(stage[cur_buf][4][k]);
-              r.wz = __uint_as_float(stage[cur_buf][5][k]);
-              r.d = __uint_as_float(stage[cur_buf][6][k]);
-              r.flags = fl;
-              r.tri = kNoTri;
-              r.u = r.v = 0.0f;
-              rd = make_raydir(r.wx, r.wy, r.wz);
-              ridx = cur_base + k;
-              cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
-              sp = 0;
-              lt = 0u;
-              has_ray = true;
-            }
-          }
-          taken += take;
-          idle = __ballot_sync(0xffffffffu, !has_ray);
-        }
-        continue;  // new rays: vote again
-      }
-      if ((tl | nl) == 0u) break;  // stream drained and every lane retired
     }
-    // 3. vote: node step or triangle step
-    // a triangle step is cheaper than a node step: PHOS_TRI_BIAS weights the vote
+    has_ray = false;
+  };
+  // 3. vote: one node step or one triangle step for the whole warp (a triangle step is cheaper than a node step:
+  // PHOS_TRI_BIAS weights the vote)
+  auto step = [&](const bool tri_work, const bool node_work, const int n_tri, const int n_node) {
+    if (kCount) {
+      if (PHOS_TRI_BIAS * n_tri >= n_node) {
+        ++w_tri;
+        l_tri += n_tri;
+      } else {
+        ++w_node;
+        l_node += n_node;
+      }
+    }
     if (PHOS_TRI_BIAS * n_tri >= n_node) {
       if (tri_work) {
         if ((lt >> 8) == 0u) {  // open the next hit leaf, nearest octant first
@@ -315,10 +329,179 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
         cur = make_uint2(h.child_base, h.imask | (h.inner << 8));
       }
     }
+  };
+
+  // ---- phase 1: the stream still has rays for this warp --------------------------------------------------------
+  for (;;) {
+    if (kCount) ++w_iter;
+    // 1. what every lane wants to do next (two ballots drive everything else)
+    const bool tri_work = has_ray && lt != 0u;
+    const bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
+    const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
+    const unsigned nl = __ballot_sync(0xffffffffu, node_work);
+    const int n_tri = __popc(tl), n_node = __popc(nl);  // disjoint sets: the rest of the warp is without work
+    // 2. enough lanes without work (finished rays or empty lanes): retire and refill from the chunk
+    if (32 - n_tri - n_node >= kRefillMin) {
+      if (has_ray && !tri_work && !node_work) retire();
+      if (taken < cur_cnt || nxt_cnt != 0) {
+        unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+        while (idle) {
+          if (taken == cur_cnt && !advance()) break;
+          const uint32_t rank = __popc(idle & lt_mask);
+          const uint32_t take = min((uint32_t)__popc(idle), cur_cnt - taken);
+          if (!has_ray && rank < take) {
+            const uint32_t k = taken + rank;
+            const uint32_t fl = stage[cur_buf][7][k];
+            if (!(fl & PHOS_MASKED)) {  // MASKED rays are consumed without being traced
+              r.ox = __uint_as_float(stage[cur_buf][0][k]);
+              r.oy = __uint_as_float(stage[cur_buf][1][k]);
+              r.oz = __uint_as_float(stage[cur_buf][2][k]);
+              r.wx = __uint_as_float(stage[cur_buf][3][k]);
+              r.wy = __uint_as_float(stage[cur_buf][4][k]);
+              r.wz = __uint_as_float(stage[cur_buf][5][k]);
+              r.d = __uint_as_float(stage[cur_buf][6][k]);
+              r.flags = fl;
+              r.tri = kNoTri;
+              r.u = r.v = 0.0f;
+              rd = make_raydir(r.wx, r.wy, r.wz);
+              ridx = cur_base + k;
+              cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
+              sp = 0;
+              lt = 0u;
+              has_ray = true;
+              if (kCount) ++n_rays;
+            }
+          }
+          taken += take;
+          idle = __ballot_sync(0xffffffffu, !has_ray);
+        }
+        continue;  // new rays: vote again
+      }
+      if (PHOS_TAIL_SHARE || (tl | nl) == 0u) break;  // nothing left to refill from: phase 2 (or: every lane retired)
+    }
+    step(tri_work, node_work, n_tri, n_node);
   }
+
+#if PHOS_TAIL_SHARE
+  // ---- phase 2: nothing left to refill from — lanes without work help the lanes that still have a ray ---------------
+  // A helper holds a copy of the ray (flag bit 31, `ridx` = the lane that owns the ray) and one group of pending siblings
+  // taken off the owner's stack (the same ray, a disjoint part of the tree); when it runs out of work its hit is merged
+  // into the owner's with the ordinary acceptance rule (closest, ties to the lower order; any-hit: the verdict), and the
+  // owner writes the ray once no helper is left.  The longest ray of a warp no longer runs on one lane while 31 wait.
+  for (;;) {
+    if (kCount) ++w_iter;
+    bool tri_work = has_ray && lt != 0u;
+    bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
+    unsigned tl = __ballot_sync(0xffffffffu, tri_work);
+    unsigned nl = __ballot_sync(0xffffffffu, node_work);
+#ifdef PHOS_TAIL_PROBE
+    ++pr_iters;
+    pr_lanes += __popc(tl | nl);
+#endif
+    if ((tl | nl) != 0xffffffffu) {
+      // helpers that are done hand their record to the owner
+      unsigned fh = __ballot_sync(0xffffffffu, has_ray && !tri_work && !node_work && (r.flags & kHelper));
+      bool changed = fh != 0u;
+      while (fh) {
+        const int h = __ffs(fh) - 1;
+        fh &= fh - 1u;
+        const uint32_t own = __shfl_sync(0xffffffffu, ridx, h);
+        const float hd = __shfl_sync(0xffffffffu, r.d, h), hu = __shfl_sync(0xffffffffu, r.u, h), hv = __shfl_sync(0xffffffffu, r.v, h);
+        const uint32_t ht = __shfl_sync(0xffffffffu, r.tri, h);
+        if (lane == own && ht != kNoTri && ht != r.tri) {
+          if (r.flags & PHOS_SHADOW) {  // any-hit: the helper accepted a triangle — occluded; the owner's own traversal stops
+            r.flags |= PHOS_HIT;
+            r.d = fminf(r.d, hd);
+            r.tri = ht;
+            lt = 0u;
+            cur.y = 0u;
+            sp = 0;
+          } else {
+            accept_hit(P.accel, r, hd, hu, hv, ht);
+          }
+        }
+        if ((int)lane == h) has_ray = false;
+      }
+      // owners that are done and have no helper left write their ray
+      const bool busy = has_ray && (lt != 0u || (cur.y >> 8) != 0u || sp != 0);
+      const uint32_t group = !has_ray ? 32u + lane : (r.flags & kHelper) ? ridx : lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, group);
+      const bool leaves = has_ray && !busy && !(r.flags & kHelper) && peers == (1u << lane);
+      if (leaves) retire();
+      changed = changed || __any_sync(0xffffffffu, leaves);  // (warp-uniform: it guards warp collectives below)
+      // free lanes take a group of pending siblings each from the lanes that can spare one: the top entry of the stack,
+      // or, with an empty stack, all but the nearest pending child of the current group
+      const unsigned pend = cur.y >> 8;
+      const bool can_give = busy && ((sp > 0 && (sp > 1 || pend != 0u || lt != 0u)) || (pend & (pend - 1u)) != 0u);  // and keep some
+      const unsigned idle = __ballot_sync(0xffffffffu, !has_ray), don = __ballot_sync(0xffffffffu, can_give);
+      if (idle == 0xffffffffu) break;  // every lane retired
+      if (idle != 0u && don != 0u) {
+        const int pairs = min(__popc(idle), __popc(don));
+        const bool take = !has_ray && __popc(idle & lt_mask) < pairs;
+        const bool give = can_give && __popc(don & lt_mask) < pairs;
+        uint2 g = make_uint2(0u, 0u);
+        if (give) {
+          if (sp > 0) {
+            g = pop();
+          } else {
+            const unsigned near = pend & (0u - pend);
+            g = make_uint2(cur.x, (cur.y & 0xffu) | ((pend ^ near) << 8));
+            cur.y = (cur.y & 0xffu) | (near << 8);
+          }
+        }
+        const int from = take ? (int)__fns(don, 0, __popc(idle & lt_mask) + 1) : (int)lane;
+        const uint32_t gx = __shfl_sync(0xffffffffu, g.x, from), gy = __shfl_sync(0xffffffffu, g.y, from);
+        const float ox = __shfl_sync(0xffffffffu, r.ox, from), oy = __shfl_sync(0xffffffffu, r.oy, from), oz = __shfl_sync(0xffffffffu, r.oz, from);
+        const float wx = __shfl_sync(0xffffffffu, r.wx, from), wy = __shfl_sync(0xffffffffu, r.wy, from), wz = __shfl_sync(0xffffffffu, r.wz, from);
+        const float dd = __shfl_sync(0xffffffffu, r.d, from), uu = __shfl_sync(0xffffffffu, r.u, from), vv = __shfl_sync(0xffffffffu, r.v, from);
+        const uint32_t tt = __shfl_sync(0xffffffffu, r.tri, from), ff = __shfl_sync(0xffffffffu, r.flags, from);
+        const uint32_t oo = __shfl_sync(0xffffffffu, (r.flags & kHelper) ? ridx : lane, from);
+        if (take) {
+          r.ox = ox; r.oy = oy; r.oz = oz;
+          r.wx = wx; r.wy = wy; r.wz = wz;
+          r.d = dd; r.u = uu; r.v = vv;
+          r.tri = tt;
+          r.flags = ff | kHelper;
+          rd = make_raydir(wx, wy, wz);
+          ridx = oo;
+          cur = make_uint2(gx, gy);
+          sp = 0;
+          lt = 0u;
+          has_ray = true;
+        }
+        changed = true;
+      }
+      if (changed) {  // vote again
+        tri_work = has_ray && lt != 0u;
+        node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
+        tl = __ballot_sync(0xffffffffu, tri_work);
+        nl = __ballot_sync(0xffffffffu, node_work);
+      }
+    }
+    step(tri_work, node_work, __popc(tl), __popc(nl));
+  }
+#endif
+#ifdef PHOS_TAIL_PROBE
+  if (lane == 0 && P.probe) {
+    unsigned long long* o = P.probe + 5ull * (blockIdx.x * kTraceWarps + warp);
+    o[0] = pr_start;
+    o[1] = pr_dry;
+    o[2] = probe_now();
+    o[3] = pr_iters;
+    o[4] = pr_lanes;
+  }
+#endif
   if (kCount) {
     atomicAdd(P.counters, (unsigned long long)n_nodes);
     atomicAdd(P.counters + 1, (unsigned long long)n_tris);
+    atomicAdd(P.counters + 7, (unsigned long long)n_rays);
+    if (lane == 0) {
+      atomicAdd(P.counters + 2, (unsigned long long)w_node);
+      atomicAdd(P.counters + 3, (unsigned long long)w_tri);
+      atomicAdd(P.counters + 4, (unsigned long long)l_node);
+      atomicAdd(P.counters + 5, (unsigned long long)l_tri);
+      atomicAdd(P.counters + 6, (unsigned long long)w_iter);
+    }
   }
 }
 

@@ -134,7 +134,7 @@ __device__ __forceinline__ void shade_nee_slot(const FrameArgs& A, const phos_ra
   v3 wi = sub(L, so);
   const float l2 = __fmaf_rn(wi.x, wi.x, __fmaf_rn(wi.y, wi.y, __fmul_rn(wi.z, wi.z)));
   const float dist = sqrtf(l2) - 0.0001f;
-  const float ool = 1.0f / sqrtf(l2);  // the reference multiplies by the ~12-bit rcpps here (simd/vector.hpp:126-133)
+  const float ool = inv_length(A.cam, l2);  // the reference multiplies by the ~12-bit rcpps here (simd/vector.hpp:126-133)
   wi = V(wi.x * ool, wi.y * ool, wi.z * ool);
   const bool ish = __fmaf_rn(n.x, wi.x, __fmaf_rn(n.y, wi.y, __fmul_rn(n.z, wi.z))) >= 0.0f;  // simd::in_same_hemisphere
   sh.px[i] = so.x;

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -130,6 +131,7 @@ class CudaDevice:
         if not self._ctx:
             raise PhosError(self._L.phos_cuda_last_error(None).decode())
         self.accel = None
+        self.has_comm = False
 
     # ---- xpu_t -----------------------------------------------------------------------------------
     @staticmethod
@@ -191,6 +193,13 @@ class CudaDevice:
         self._check(self._L.phos_cuda_trace_count(self._ctx, C.byref(rays.s), rays.n, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def trace_profile(self, rays: DeviceRays, n: int | None = None) -> dict:
+        """One launch of the counting instantiation: per-lane fetch counts and warp-level step statistics."""
+        out = (C.c_uint64 * 8)()
+        self._check(self._L.phos_cuda_trace_profile(self._ctx, C.byref(rays.s), rays.n if n is None else n, out))
+        keys = ("nodes", "tris", "warp_node_steps", "warp_tri_steps", "lanes_node_steps", "lanes_tri_steps", "warp_iterations", "rays")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def upload_scene(self, scene: Scene) -> None:
         d = scene.desc()
         self._check(self._L.phos_cuda_upload_scene(self._ctx, C.byref(d)))
@@ -230,6 +239,11 @@ class CudaDevice:
         self._check(self._L.phos_cuda_film_read(self._ctx, out.ctypes.data, x, y, w, h))
         return out
 
+    def reference_normalize(self, on: bool = True) -> None:
+        """Normalise camera / shadow-ray directions through the host's RCPSS, as the reference's vector3_t<8>::normalize
+        does (src/math/simd/vector.hpp:126-133): images then match the reference's cpu_t instead of exact arithmetic."""
+        self._check(self._L.phos_cuda_reference_normalize(self._ctx, 1 if on else 0))
+
     def enable_normals(self, on: bool = True) -> None:
         """Request the NORMALS channel (render_buffer_t::NORMALS, cpu.cpp:97,194-196) for the following renders."""
         self._check(self._L.phos_cuda_enable_normals(self._ctx, 1 if on else 0))
@@ -245,6 +259,23 @@ class CudaDevice:
         p, n = C.c_void_p(0), C.c_uint64(0)
         self._check(self._L.phos_cuda_film_device_ptr(self._ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    # ---- multi-GPU: the per-frame film reduce (one process per GPU) ---------------------------------------
+    def comm_init(self, dist) -> None:
+        """Create this context's NCCL communicator over the ranks of an initialised ``torch.distributed`` group: rank 0
+        draws the unique id (ncclGetUniqueId), the group ships its 128 bytes, every rank joins (ncclCommInitRank)."""
+        ident = (C.c_uint8 * 128)()
+        if dist.get_rank() == 0:
+            self._check(self._L.phos_cuda_comm_unique_id(ident))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        self._check(self._L.phos_cuda_comm_init(self._ctx, dist.get_world_size(), dist.get_rank(), ident))
+        self.has_comm = True
+
+    def film_reduce(self, root: int = 0) -> None:
+        """ncclReduce(sum) of the device film onto `root`, enqueued behind the frame's kernels (asynchronous)."""
+        self._check(self._L.phos_cuda_film_reduce(self._ctx, root))
 
     def flush_l2(self) -> None:
         self._check(self._L.phos_cuda_flush_l2(self._ctx))
@@ -284,7 +315,8 @@ class CudaDevice:
 
 
 def pinned_ray_batch(n: int) -> RayBatch:
-    """A RayBatch whose arrays live in page-locked host memory (fast, truly asynchronous copies)."""
+    """A RayBatch whose arrays live in one page-locked slab (fast, truly asynchronous copies).  The slab is released by
+    ``batch.free()`` or when the batch is collected; ``copy()`` / ``slice()`` return ordinary pageable batches."""
     L = _lib.load()
     r = RayBatch(0)
     r.n = int(n)
@@ -293,6 +325,8 @@ def pinned_ray_batch(n: int) -> RayBatch:
     if not base:
         raise PhosError("phos_cuda_host_alloc failed")
     r._pinned = base
+    r._release = weakref.finalize(r, L.phos_cuda_host_free, base)  # the arrays are views: do not keep them past the batch
+    r.free = r._release
     # one slab, constant stride, in the library's own array order: phos_cuda_trace then moves a chunk with a
     # single pitched copy per direction (see csrc/phos_cuda.cu)
     order = ("px", "py", "pz", "wx", "wy", "wz", "d", "flags", "mesh", "face", "u", "v")

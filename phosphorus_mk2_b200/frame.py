@@ -42,6 +42,16 @@ class Tiles:
             self._cursor = b
         return self.tiles[a:b]
 
+    def remaining(self) -> int:
+        with self._lock:
+            return self.size - self._cursor
+
+    def take_guided(self, peers: int = 1, lo: int = 64, hi: int = 1024):
+        """The claim of integration/cuda.cpp (take_tiles): half of this device's share of what is left, at least `lo`
+        tiles (a wavefront over few pixels idles in its launch tails), at most `hi` — so that the devices sharing the
+        queue (session.cpp:85-99) finish together."""
+        return self.next_chunk(min(hi, max(lo, self.remaining() // (2 * max(1, peers)))))
+
 
 class MemoryFilm:
     """film_t<>: an in-memory sink; ``add_tile`` may be called from several device threads."""
@@ -70,21 +80,33 @@ class DeviceThread:
     """What cpu_t::start spawns per worker, for one GPU: drain the shared tile queue in chunks,
     render each chunk as one wavefront, hand every finished tile to the film sink."""
 
-    def __init__(self, dev: CudaDevice, frame: FrameState, chunk_tiles: int = 4096, sample_range=None):
+    def __init__(self, dev: CudaDevice, frame: FrameState, chunk_tiles: int = 1024, sample_range=None, peers: int = 1):
         self.dev, self.frame, self.chunk, self.error = dev, frame, chunk_tiles, None
         self.sample_range = sample_range or (0, frame.spp)
+        self.peers, self.tiles_done, self.claims = peers, 0, 0
         self.thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
         try:
             f = self.frame
-            while True:
-                tiles = f.tiles.next_chunk(self.chunk)
-                if not tiles:
-                    break
-                self.dev.render(tiles, self.sample_range[0], self.sample_range[1], f.spp, f.seed)
-                for (x, y, w, h) in tiles:
-                    f.film.add_tile((x, y), (w, h), self.dev.film_read(x, y, w, h))
+            W = f.tiles.width
+
+            def claim():
+                tiles = f.tiles.take_guided(self.peers, hi=self.chunk)
+                if tiles:
+                    self.dev.render(tiles, self.sample_range[0], self.sample_range[1], f.spp, f.seed)  # asynchronous
+                return tiles
+
+            cur = claim()
+            while cur:
+                y0, y1 = min(t[1] for t in cur), max(t[1] + t[3] for t in cur)
+                rows = self.dev.film_read(0, y0, W, y1 - y0)  # the chunk's film rows, once (blocks until rendered)
+                nxt = claim()                                  # the GPU renders the next chunk while the host slices this one
+                for (x, y, w, h) in cur:
+                    f.film.add_tile((x, y), (w, h), rows[y - y0:y - y0 + h, x:x + w])
+                self.tiles_done += len(cur)
+                self.claims += 1
+                cur = nxt
         except Exception as e:  # surfaced by join(), like an exception escaping a reference worker
             self.error = e
 
@@ -111,8 +133,16 @@ def tiles_of_rank(tiles, rank: int, world: int):
 
 
 def samples_of_rank(spp: int, rank: int, world: int):
-    """Sample-partitioned frame: rank r renders the contiguous sample range [r*spp/world, (r+1)*spp/world)."""
+    """Sample-partitioned frame: rank r renders the contiguous sample range [r*spp/world, (r+1)*spp/world) — empty for
+    some ranks when spp < world (render_partition then renders nothing on that rank: it only joins the reduce)."""
     return (spp * rank) // world, (spp * (rank + 1)) // world
+
+
+def render_partition(dev: CudaDevice, tiles, sample_range, spp_total: int, seed: int = 0) -> None:
+    """This rank's share of a frame into the (cleared) device film; a rank whose share is empty contributes zeros."""
+    dev.film_clear()
+    if tiles and sample_range[1] > sample_range[0]:
+        dev.render(tiles, sample_range[0], sample_range[1], spp_total, seed)
 
 
 def reduce_film(film, dist, root: int = 0):
@@ -120,6 +150,8 @@ def reduce_film(film, dist, root: int = 0):
     tensors, gloo for the CPU tests).  Disjoint tiles make the sum a gather; weighted sample ranges
     make it the average.  `film` is a torch tensor (device film wrapped zero-copy, or a host film)."""
     dist.reduce(film, dst=root, op=dist.ReduceOp.SUM)
+    if dist.get_rank() == root:  # every rank wrote alpha = 1 where it rendered: a sample-partitioned sum leaves `world` there
+        film.view(-1, 4)[:, 3].clamp_(max=1.0)
     return film
 
 

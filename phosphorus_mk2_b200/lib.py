@@ -60,6 +60,7 @@ SYMBOLS = {
     "phos_cuda_trace": (_I, [_VP, _RP, _U64]),
     "phos_cuda_trace_device": (_I, [_VP, _RP, _U64]),
     "phos_cuda_trace_count": (_I, [_VP, _RP, _U64, C.POINTER(_U64), C.POINTER(_U64)]),
+    "phos_cuda_trace_profile": (_I, [_VP, _RP, _U64, C.POINTER(_U64)]),
     "phos_cuda_rays_alloc": (_I, [_VP, _U64, _RP]),
     "phos_cuda_rays_free": (_I, [_VP, _RP]),
     "phos_cuda_rays_upload": (_I, [_VP, _RP, _RP, _U64]),
@@ -83,6 +84,12 @@ SYMBOLS = {
     "phos_cuda_film_read": (_I, [_VP, _VP, _U32, _U32, _U32, _U32]),
     "phos_cuda_enable_normals": (_I, [_VP, C.c_int]),
     "phos_cuda_film_read_normals": (_I, [_VP, _VP, _U32, _U32, _U32, _U32]),
+    "phos_cuda_reference_normalize": (_I, [_VP, _I]),
+    "phos_cuda_comm_unique_id": (_I, [_VP]),
+    "phos_cuda_comm_init": (_I, [_VP, _I, _I, _VP]),
+    "phos_cuda_comm_adopt": (_I, [_VP, _VP, _I]),
+    "phos_cuda_comm_destroy": (None, [_VP]),
+    "phos_cuda_film_reduce": (_I, [_VP, _I]),
 }
 
 _libs: dict = {}

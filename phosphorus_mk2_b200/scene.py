@@ -58,6 +58,7 @@ class PhosSceneDesc(C.Structure):
         ("materials", C.POINTER(PhosMaterial)),
         ("camera", PhosCamera),
         ("environment", C.c_int32),
+        ("face_smooth", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -107,6 +108,7 @@ class Mesh:
     sets: list  # [(material_id, face_index_array)] in set order
     smooth: bool = False
     normals: np.ndarray | None = None  # (nv, 3) float32, per vertex
+    face_smooth: np.ndarray | None = None  # (nf,) bool: builder_t::add_face(a, b, c, smooth) per face (overrides `smooth`)
 
     def __post_init__(self):
         self.vertices = np.ascontiguousarray(self.vertices, dtype=np.float32).reshape(-1, 3)
@@ -115,7 +117,11 @@ class Mesh:
         if self.normals is not None:
             self.normals = np.ascontiguousarray(self.normals, dtype=np.float32).reshape(-1, 3)
             assert len(self.normals) == len(self.vertices)
-        if self.smooth:
+        if self.face_smooth is not None:
+            self.face_smooth = np.ascontiguousarray(self.face_smooth, dtype=np.uint8).ravel()
+            assert len(self.face_smooth) == len(self.faces)
+            self.smooth = bool(self.face_smooth.all())
+        if self.smooth or (self.face_smooth is not None and self.face_smooth.any()):
             assert self.normals is not None, "smooth faces interpolate per-vertex normals"
 
     @property
@@ -190,10 +196,19 @@ class Scene:
         vertices = np.concatenate([m.vertices for m in self.meshes]).astype(np.float32, copy=False)
         has_normals = all(m.normals is not None for m in self.meshes)
         normals = np.concatenate([m.normals for m in self.meshes]) if has_normals else None
+        def smooth_kind(m):  # 0 flat, 1 smooth, 2 mixed (per face)
+            if m.face_smooth is None or m.face_smooth.all() or not m.face_smooth.any():
+                return 1 if (m.smooth or (m.face_smooth is not None and len(m.face_smooth) and m.face_smooth.all())) else 0
+            return 2
+
+        smooth = np.array([smooth_kind(m) for m in self.meshes], np.uint8)
         if not has_normals:
-            assert not any(m.smooth for m in self.meshes), "smooth meshes need normals on every mesh"
+            assert not smooth.any(), "smooth faces need normals on every mesh"
         faces = np.concatenate([m.faces for m in self.meshes]).astype(np.uint32, copy=False)
-        smooth = np.array([1 if m.smooth else 0 for m in self.meshes], np.uint8)
+        face_smooth = None
+        if (smooth == 2).any():
+            face_smooth = np.concatenate([m.face_smooth if m.face_smooth is not None else np.full(len(m.faces), 1 if m.smooth else 0, np.uint8)
+                                          for m in self.meshes]).astype(np.uint8)
         set_material, set_faces_l = [], []
         for m in self.meshes:
             for mat, f in m.sets:
@@ -246,6 +261,7 @@ class Scene:
         d.camera.film_width = cam.film_width
         d.camera.film_height = cam.film_height
         d.environment = -1 if self.environment is None else int(self.environment)
-        self._keep = (vert_offset, vertices, normals, face_offset, faces, smooth, set_offset, set_material,
+        d.face_smooth = p(face_smooth, C.c_uint8)
+        self._keep = (face_smooth, vert_offset, vertices, normals, face_offset, faces, smooth, set_offset, set_material,
                       set_face_offset, set_faces, mats)
         return d

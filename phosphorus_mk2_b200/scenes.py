@@ -48,7 +48,7 @@ def _box(verts, faces, lo, hi, rot_y=0.0, outward=True):
     _quad(verts, faces, P(-1, -1, -1), P(1, -1, -1), P(1, -1, 1), P(-1, -1, 1), N(0, -1, 0))
 
 
-def cornell_box(width: int = 512, height: int = 512) -> Scene:
+def cornell_box(width: int = 512, height: int = 512, light_y: float = 1.98) -> Scene:
     """Config 1: 38-triangle Cornell box, two area lights (SURVEY.md §8d "Config 1").
 
     5 wall quads (10 tris), short box + tall box (12 each), 2 emissive quads under the ceiling (4).
@@ -78,8 +78,10 @@ def cornell_box(width: int = 512, height: int = 512) -> Scene:
     s.add(Mesh(np.array(v), np.array(f), [(glossy, np.arange(12))]))
 
     v, f = [], []
-    _quad(v, f, (-0.6, 1.98, -0.25), (-0.1, 1.98, -0.25), (-0.1, 1.98, 0.25), (-0.6, 1.98, 0.25), (0, -1, 0))
-    _quad(v, f, (0.1, 1.98, -0.25), (0.6, 1.98, -0.25), (0.6, 1.98, 0.25), (0.1, 1.98, 0.25), (0, -1, 0))
+    # (light_y well below the ceiling takes the 1 / d^2 spikes of next-event estimation onto the ceiling 2 cm above the
+    # lights out of the image: plain means then converge fast enough for percent-level comparisons)
+    _quad(v, f, (-0.6, light_y, -0.25), (-0.1, light_y, -0.25), (-0.1, light_y, 0.25), (-0.6, light_y, 0.25), (0, -1, 0))
+    _quad(v, f, (0.1, light_y, -0.25), (0.6, light_y, -0.25), (0.6, light_y, 0.25), (0.1, light_y, 0.25), (0, -1, 0))
     # two face sets -> two area lights (one light per emissive face set, src/mesh.cpp:108-116)
     s.add(Mesh(np.array(v), np.array(f), [(light, np.arange(0, 2)), (light, np.arange(2, 4))]))
 
@@ -127,6 +129,21 @@ def sphere_field(grid: int = 16, seg_u: int = 64, seg_v: int = 32, width: int = 
     ext = float(grid)
     cam.to_world = Camera.look_at((0.0, 0.62 * ext, 0.78 * ext), (0.0, 0.0, -0.02 * ext))
     s.camera = cam
+    return s
+
+
+def mixed_shading_spheres(width: int = 64, height: int = 48) -> Scene:
+    """2 x 2 spheres whose faces alternate between smooth and flat shading in bands of rows — the per-face flag of
+    mesh_t::builder_t::add_face(a, b, c, smooth) (src/mesh.hpp:46-66, src/mesh.cpp:202-206) — under an emissive quad."""
+    s = sphere_field(2, 24, 12, width, height, smooth=True)
+    for k, m in enumerate(s.meshes):
+        band = (np.arange(len(m.faces)) // 48 + k) % 2  # 24 quads x 2 triangles per row of the sphere
+        m.face_smooth = band.astype(np.uint8)
+        m.smooth = False
+    light = s.add_material(Material(MAT_EMITTER, (1.0, 0.9, 0.8), power=30.0))
+    v = np.array([[-1.5, 2.0, -1.5], [1.5, 2.0, -1.5], [1.5, 2.0, 1.5], [-1.5, 2.0, 1.5]], np.float32)
+    nrm = np.tile(np.array([[0, -1, 0]], np.float32), (4, 1))
+    s.add(Mesh(v, np.array([[0, 1, 2], [0, 2, 3]]), [(light, np.arange(2))], smooth=False, normals=nrm))
     return s
 
 

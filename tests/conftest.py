@@ -41,6 +41,16 @@ def reflib():
     return RefLib()
 
 
+@pytest.fixture(scope="session")
+def reflib_cuda():
+    """The same reference objects + the drop-in GPU device (integration/cuda.cpp, integration/xpu_discover.patch)
+    linked against libphos_cuda.so: oracle/_ref/libphos_ref_cuda.so."""
+    from oracle.pyoracle import RefLib
+    if not RefLib.available(cuda=True):
+        pytest.skip("oracle/_ref/libphos_ref_cuda.so not built (needs /root/reference at build time)")
+    return RefLib(cuda=True)
+
+
 def _build_emul(defs):
     import ctypes as C
     from phosphorus_mk2_b200.rays import PhosRays

@@ -55,6 +55,7 @@ def test_film_reduce_two_ranks_gloo(tmp_path):
         W, H = 96, 64
         tiles = Tiles.make(W, H).tiles
         full = np.arange(W * H * 4, dtype=np.float32).reshape(H, W, 4)
+        full[..., 3] = 1.0  # alpha = 1 where rendered
         # tile-partitioned: own tiles carry the final value, the rest is zero
         film = np.zeros_like(full)
         for (x, y, w, h) in tiles_of_rank(tiles, r, n):
@@ -65,7 +66,9 @@ def test_film_reduce_two_ranks_gloo(tmp_path):
             assert np.array_equal(film, full)
         # sample-partitioned: each rank holds its weighted share of every pixel
         a, b = samples_of_rank(16, r, n)
-        t = torch.from_numpy(full * ((b - a) / 16.0))
+        share = full * ((b - a) / 16.0)
+        share[..., 3] = 1.0  # every rank renders every pixel: the sum of the alphas is clamped back to 1
+        t = torch.from_numpy(share)
         reduce_film(t, dist, 0)
         if r == 0:
             assert np.allclose(t.numpy(), full, rtol=1e-6)

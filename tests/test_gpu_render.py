@@ -254,3 +254,121 @@ def test_two_contexts_emulate_two_ranks():
             assert np.array_equal(total[..., :3], whole[..., :3])  # disjoint tiles: the sum is a gather
         else:
             assert np.allclose(total[..., :3], whole[..., :3], rtol=2e-6, atol=1e-7)  # (a + b) + (c + d) vs a + b + c + d
+
+
+def test_per_face_smooth_flag(oracle):
+    """Meshes mixing smooth and flat faces (phos_scene_desc::face_smooth, mesh_smooth = 2): image and NORMALS channel
+    against the oracle."""
+    sc = scenes.mixed_shading_spheres(70, 50)
+    acc = Accel(sc)
+    want_n = np.zeros((50, 70, 3), np.float32)
+    want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), 4, 1, 4, seed=5, normals=want_n)
+    dev = CudaDevice.make(Options(4, 1, 4), 0)
+    dev.preprocess(sc, acc)
+    dev.upload_scene(sc)
+    dev.enable_normals()
+    dev.render(make_tiles(70, 50), 0, 4, 4, 5)
+    got, got_n = dev.film_read(), dev.film_read_normals()
+    dev.close()
+    assert np.abs(got_n - want_n).max() < 1e-5
+    assert mean_rel_err(got, want) < 1e-3
+
+
+def test_film_reduce_inside_the_library_single_rank():
+    """phos_cuda_comm_* / phos_cuda_film_reduce with a one-rank communicator: the reduce is the identity on the colours
+    and clamps alpha (the N-rank case runs under torchrun in test_gpu_multi.py when the box has >= 2 GPUs)."""
+    import ctypes as C
+    sc = scenes.cornell_box(64, 64)
+    acc = Accel(sc)
+    dev = CudaDevice.make(Options(4, 1, 3), 0)
+    dev.preprocess(sc, acc)
+    dev.upload_scene(sc)
+    ident = (C.c_uint8 * 128)()
+    dev._check(dev._L.phos_cuda_comm_unique_id(ident))
+    dev._check(dev._L.phos_cuda_comm_init(dev._ctx, 1, 0, ident))
+    dev.render(make_tiles(64, 64), 0, 4, 4, 7)
+    before = dev.film_read()
+    dev.film_reduce(0)
+    after = dev.film_read()
+    with pytest.raises(PhosError):
+        dev.film_reduce(1)  # root outside the communicator
+    dev.close()
+    assert np.array_equal(before, after) and (after[..., 3] == 1.0).all()
+
+
+def test_pinhole_camera_rays_are_bit_identical_to_the_oracle(oracle):
+    """phos_cuda_camera_rays, pinhole branch (camera.hpp:113-152), tile by tile in the reference's 32 x 32 order with
+    partial tiles, a jitter other than the centre, and a rotated / translated camera: every origin and direction bit
+    for bit the oracle's restatement (exact 1 / sqrt on both sides; no transcendental function is involved)."""
+    from phosphorus_mk2_b200.scene import Camera
+    sc = scenes.sphere_field(2, 16, 8, 150, 70)
+    sc.camera.to_world = Camera.look_at((1.3, 2.1, 3.7), (0.2, -0.1, 0.4))
+    acc = Accel(sc)
+    dev = CudaDevice.make(Options(), 0)
+    dev.preprocess(sc, acc)
+    dev.upload_scene(sc)
+    tiles = make_tiles(150, 70)
+    dr = dev.device_rays(150 * 70)
+    for jx, jy in ((0.5, 0.5), (0.125, 0.875)):
+        dev.camera_rays(tiles, dr, jx, jy)
+        got = dr.download()
+        o = 0
+        for (x, y, w, h) in tiles:
+            want = oracle.camera_rays(sc.camera, x, y, w, h, jx, jy)
+            for f in ("px", "py", "pz", "wx", "wy", "wz", "d", "flags"):
+                assert np.array_equal(getattr(got, f)[o:o + w * h].view(np.uint32), getattr(want, f).view(np.uint32)), (f, x, y)
+            o += w * h
+    dr.free()
+    dev.close()
+
+
+def test_reference_normalize_reproduces_the_rcpps_images(oracle):
+    """phos_cuda_reference_normalize: camera and shadow-ray directions normalised through the host's RCPSS (sampled into a
+    table, rcp_table.cpp) — the image of the oracle's rcp_mode 2 (RCPSS normalisation, exact traversal) at matched
+    samples, and visibly darker than exact arithmetic (the reference's shadow rays overshoot into the light)."""
+    sc = scenes.cornell_box(64, 64)
+    acc = Accel(sc)
+    nodes, packets = acc.nodes_array(), acc.packets_array()
+    dev = CudaDevice.make(Options(16, 1, 4), 0)
+    dev.reference_normalize(True)
+    dev.preprocess(sc, acc)
+    dev.upload_scene(sc)
+    dr = dev.device_rays(64 * 64)
+    dev.camera_rays([(0, 0, 64, 64)], dr, 0.5, 0.5)
+    rays = dr.download()
+    dr.free()
+    wp, ww = oracle.camera_rays_lens(sc, 0, 0, 64, 64, 0.5, 0.5, np.full(4096, 0.5, np.float32), np.full(4096, 0.5, np.float32), rcp_mode=True)
+    assert np.array_equal(np.stack([rays.wx, rays.wy, rays.wz], 1).view(np.uint32), ww.view(np.uint32))  # RCPSS bit for bit
+    dev.render(make_tiles(64, 64), 0, 16, 16, 5)
+    got = dev.film_read()
+    dev.reference_normalize(False)
+    dev.film_clear()
+    dev.render(make_tiles(64, 64), 0, 16, 16, 5)
+    exact = dev.film_read()
+    dev.close()
+    want = oracle.render(sc, nodes, packets, 16, 1, 4, seed=5, rcp_mode=2)
+    assert mean_rel_err(got, want) < 1e-3
+    assert mean_rel_err(exact, oracle.render(sc, nodes, packets, 16, 1, 4, seed=5)) < 1e-3
+    assert np.median(exact[..., :3]) > 1.05 * np.median(got[..., :3])
+
+
+def test_reduced_config4_scene_matches_oracle(oracle):
+    """BASELINE config 4's scene family at a size the oracle renders in seconds: displaced terrain with 10 % GGX face
+    bands (roughness 0.2) under the sky emitter, depth 8."""
+    sc = scenes.terrain(n=129, glossy_fraction=0.1, width=96, height=64)
+    acc = Accel(sc)
+    want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), 8, 1, 8, seed=13)
+    got, _ = render_gpu(sc, acc, 8, 8, 13)
+    assert np.isfinite(got).all() and want[..., :3].mean() > 1e-3
+    assert mean_rel_err(got, want) < 1e-3
+
+
+def test_reduced_config5_scene_matches_oracle(oracle):
+    """BASELINE config 5's scene family: a field of baked copies of one object (one mesh_t each: 9 meshes + the light),
+    sample-partitioned over two calls like two ranks."""
+    sc = scenes.instanced_field(grid=3, width=96, height=64)
+    acc = Accel(sc)
+    want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), 8, 1, 6, seed=17)
+    got, _ = render_gpu(sc, acc, 8, 6, 17, ranges=[(0, 4), (4, 8)])
+    assert np.isfinite(got).all() and want[..., :3].mean() > 1e-3
+    assert mean_rel_err(got, want) < 1e-3
