@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/phos_cuda.h"
+#include "../../include/phos_scene.h"
 
 namespace phos {
 
@@ -34,6 +35,7 @@ struct phos_ctx {
   int device = 0;
   int sm_count = 0;
   int trace_blocks_per_sm = 1;
+  size_t max_pitch = 0;  // cudaDeviceProp::memPitch: the longest row a pitched copy accepts
   phos_options opt = {16, 16, 9};
   std::string err;
   cudaStream_t stream = nullptr;
@@ -68,4 +70,7 @@ int launch_trace(phos_ctx* ctx, const phos_rays& dev, uint64_t n, cudaStream_t s
 void phos_render_release(phos_ctx* ctx);  // render.cu
 void comm_release(phos_ctx* ctx);         // comm.cu
 bool sample_host_rcp(std::vector<float>& table, int& bits);  // rcp_table.cpp
+// every vertex index of every face below its mesh's vertex count (a malformed scene must fail with PHOS_ERR_INVALID on
+// the host, not fault on the device: a device fault is sticky and kills the context)
+bool scene_indices_ok(const phos_scene_desc* d);
 }  // namespace phos

@@ -404,6 +404,7 @@ extern "C" int phos_cuda_build_accel(phos_ctx* ctx, const phos_scene_desc* d) {
   if (nm == 0 || !d->vert_offset || !d->vertices || !d->face_offset || !d->faces || !d->set_offset || !d->set_material ||
       !d->set_face_offset || !d->set_faces)
     return fail(ctx, PHOS_ERR_INVALID, "incomplete scene description");
+  if (!scene_indices_ok(d)) return fail(ctx, PHOS_ERR_INVALID, "face with a vertex index outside its mesh");
   cudaSetDevice(ctx->device);
   const auto t0 = std::chrono::steady_clock::now();
   // triangles in the reference's numbering: mesh -> face set -> face (src/scene.cpp:58-62, src/mesh.cpp:118-128)
@@ -464,7 +465,7 @@ extern "C" int phos_cuda_build_accel(phos_ctx* ctx, const phos_scene_desc* d) {
   if (!sort_tmp.alloc(ctx, tmp_bytes, "cudaMalloc(sort)")) return PHOS_ERR_CUDA;
   cub::DeviceRadixSort::SortPairs(sort_tmp.p, tmp_bytes, keys_in.p, keys.p, vals_in.p, vals.p, (int)n, 0, 63, st);
   radix_tree_kernel<<<G, T, 0, st>>>(keys.p, (int)n, left.p, right.p, par_i.p, par_l.p);
-  cudaMemsetAsync(visits.p, 0, 4ull * n, st);
+  if (!cuda_ok(ctx, cudaMemsetAsync(visits.p, 0, 4ull * n, st), "memset (build)")) return PHOS_ERR_CUDA;
   refit_kernel<<<G, T, 0, st>>>((int)n, vals.p, tboxes.p, left.p, right.p, par_i.p, par_l.p, nboxes.p, ncount.p, visits.p);
   ctx->launches += 4;
   if (!cuda_ok(ctx, cudaGetLastError(), "build kernels")) return PHOS_ERR_CUDA;
@@ -477,9 +478,13 @@ extern "C" int phos_cuda_build_accel(phos_ctx* ctx, const phos_scene_desc* d) {
     if (out_nodes) cudaFree(out_nodes);
     return PHOS_ERR_CUDA;
   }
-  cudaMemsetAsync(counters.p, 0, 16, st);  // [0] next level count, [1] triangle cursor, [2] error
   const uint32_t root_item = 0;
-  up(items_a.p, &root_item, 4);
+  if (!cuda_ok(ctx, cudaMemsetAsync(counters.p, 0, 16, st), "memset (build)") ||  // [0] next level count, [1] triangle cursor, [2] error
+      !up(items_a.p, &root_item, 4)) {
+    cudaFree(out_nodes);
+    cudaFree(out_tris);
+    return PHOS_ERR_CUDA;
+  }
   uint32_t level_first = 0, level_count = 1, depth = 0;
   uint32_t* cur = items_a.p;
   uint32_t* nxt = items_b.p;

@@ -1,6 +1,7 @@
 // phos_cuda.cu — the C ABI of libphos_cuda.so (include/phos_cuda.h): context, acceleration-structure
 // upload, ray-stream buffers and the trace entry points.  No CPU fallback exists anywhere in this
 // library: without a CUDA device every entry point fails with PHOS_ERR_NO_DEVICE.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <sched.h>
@@ -36,6 +37,19 @@ int fail(phos_ctx* ctx, int code, const char* msg) {
   if (ctx) ctx->err = msg;
   else g_create_error = msg;
   return code;
+}
+
+bool scene_indices_ok(const phos_scene_desc* d) {
+  for (uint32_t m = 0; m < d->num_meshes; ++m) {
+    if (d->vert_offset[m + 1] < d->vert_offset[m] || d->face_offset[m + 1] < d->face_offset[m]) return false;
+    const uint32_t nv = d->vert_offset[m + 1] - d->vert_offset[m];
+    const uint32_t* f = d->faces + 3 * (size_t)d->face_offset[m];
+    const size_t n = 3 * (size_t)(d->face_offset[m + 1] - d->face_offset[m]);
+    uint32_t worst = 0;
+    for (size_t i = 0; i < n; ++i) worst = std::max(worst, f[i]);
+    if (n && worst >= nv) return false;
+  }
+  return true;
 }
 
 void free_rays(phos_rays& r) {
@@ -201,6 +215,7 @@ phos_ctx* phos_cuda_create(int device, const phos_options* options) {
   phos_ctx* ctx = new phos_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_pitch = prop.memPitch;
   if (options) ctx->opt = *options;
   else ctx->opt = phos_options{16, 16, 9};
   bool ok = cuda_ok(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -361,7 +376,7 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
                           (const char*)rays->wy, (const char*)rays->wz, (const char*)rays->d,     (const char*)rays->flags,
                           (const char*)rays->mesh, (const char*)rays->face, (const char*)rays->u, (const char*)rays->v};
   const ptrdiff_t hstride = slab[1] - slab[0];
-  bool pitched = hstride >= (ptrdiff_t)(n * 4);
+  bool pitched = hstride >= (ptrdiff_t)(n * 4) && (size_t)hstride <= ctx->max_pitch;  // longer rows take the 12-copy path
   for (int k = 2; pitched && k < 12; ++k) pitched = slab[k] - slab[k - 1] == hstride;
   // Page-locked, device-mapped host arrays (cudaHostAlloc / cudaHostRegister; under unified addressing the
   // device pointer is the host pointer): only the eight input arrays go up (32 B per ray) and the results are
@@ -378,8 +393,21 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
     sparse = sparse && cudaPointerGetAttributes(&at, last) == cudaSuccess && at.type == cudaMemoryTypeHost &&
              at.devicePointer == (void*)last;
     cudaGetLastError();  // an unregistered pointer reports an error on older drivers: not ours
+    if (sparse) {  // ... and both ends belong to ONE mapped allocation (two registered regions with a hole between them do not)
+      // (the driver entry point comes through the runtime: the library does not link libcuda, so it still loads on a box
+      // without a driver and fails in phos_cuda_create instead)
+      typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      CUdeviceptr b0 = 0, b1 = 0;
+      size_t s0 = 0, s1 = 0;
+      sparse = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
+               ((range_fn)fn)(&b0, &s0, (CUdeviceptr)(uintptr_t)slab[0]) == CUDA_SUCCESS &&
+               ((range_fn)fn)(&b1, &s1, (CUdeviceptr)(uintptr_t)last) == CUDA_SUCCESS && b0 == b1;
+      cudaGetLastError();
+    }
   }
-  int slot = 0;
+  int slot = 0, launch_rc = 0;
   bool ok = true;
   // The write-back runs on a handful of CTAs: its posted writes share the link's outbound queue with the read
   // requests of the up-copies, and a full grid starves them (measured, profiles/r01_e2e_pipeline.log: 4 CTAs
@@ -411,7 +439,11 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
          cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_cmp, L.ev_in, 0), "pipeline wait");
     if (!ok) break;
     const int rc = launch_trace(ctx, L.rays, cnt, ctx->s_cmp, ctx->d_counters + 16 + slot, false);
-    if (rc) return rc;
+    if (rc) {  // copies of earlier chunks may still be writing the caller's arrays: drain like any other failure
+      launch_rc = rc;
+      ok = false;
+      break;
+    }
     ok = cuda_ok(ctx, cudaEventRecord(L.ev_cmp, ctx->s_cmp), "pipeline record") &&
          cuda_ok(ctx, cudaStreamWaitEvent(ctx->s_out, L.ev_cmp, 0), "pipeline wait");
     if (ok && sparse && !dbg_noout) {
@@ -441,7 +473,7 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
     cudaStreamSynchronize(ctx->s_in2);
     cudaStreamSynchronize(ctx->s_cmp);
     cudaStreamSynchronize(ctx->s_out);
-    return PHOS_ERR_CUDA;
+    return launch_rc ? launch_rc : PHOS_ERR_CUDA;
   }
   return cuda_ok(ctx, cudaStreamSynchronize(ctx->s_out), "trace pipeline") ? PHOS_OK : PHOS_ERR_CUDA;
 }

@@ -194,6 +194,7 @@ int RenderState::upload(phos_ctx* ctx, const phos_scene_desc* d) {
   if (nm == 0 || !d->vert_offset || !d->vertices || !d->face_offset || !d->faces || !d->mesh_smooth || !d->set_offset ||
       !d->set_material || !d->set_face_offset || !d->set_faces || (d->num_materials && !d->materials))
     return fail(ctx, PHOS_ERR_INVALID, "incomplete scene description");
+  if (!scene_indices_ok(d)) return fail(ctx, PHOS_ERR_INVALID, "face with a vertex index outside its mesh");
   num_meshes = nm;
   num_materials = d->num_materials;
   const size_t nv = d->vert_offset[nm], nf = d->face_offset[nm];
@@ -325,7 +326,7 @@ static void release_one(Wavefront& wf) {
   free_rays(wf.rays[0]);
   free_rays(wf.rays[1]);
   free_rays(wf.shadow);
-  void* ptrs[] = {wf.slot_path[0], wf.slot_path[1], wf.count, wf.n, wf.light_pdf, wf.beta, wf.rad, wf.depth, wf.pixel};
+  void* ptrs[] = {wf.slot_path[0], wf.slot_path[1], wf.count, wf.n, wf.light_pdf, wf.beta[0], wf.beta[1], wf.rad[0], wf.rad[1], wf.rad_final, wf.pixel, wf.perm};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   wf = Wavefront();
@@ -345,10 +346,13 @@ bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixel
     get((void**)&wf.count, 16);
     get((void**)&wf.n, cap * 12);
     get((void**)&wf.light_pdf, cap * 4);
-    get((void**)&wf.beta, cap * 12);
-    get((void**)&wf.rad, cap * 12);
-    get((void**)&wf.depth, cap * 4);
+    for (int k = 0; k < 2; ++k) {
+      get((void**)&wf.beta[k], cap * 12);
+      get((void**)&wf.rad[k], cap * 12);
+    }
+    get((void**)&wf.rad_final, cap * 12);
     get((void**)&wf.pixel, std::max<uint64_t>(pixels, 1024) * 4);
+    get((void**)&wf.perm, cap * 4);
     if (!ok) {
       release_one(wf);
       return false;

@@ -25,11 +25,13 @@ struct Wavefront {
   uint32_t* count = nullptr;  // [0..1] live slots of stream 0 / 1 (device counters), [2] scratch
   float* n = nullptr;         // shading normal per slot, 3 x capacity
   float* light_pdf = nullptr; // per slot
-  float* beta = nullptr;      // per path, 3 x capacity
-  float* rad = nullptr;       // per path, 3 x capacity
-  uint32_t* depth = nullptr;  // per path
+  float* beta[2] = {nullptr, nullptr};  // per SLOT, 3 x capacity, ping-pong with the ray streams (wavefront.cu FrameArgs)
+  float* rad[2] = {nullptr, nullptr};   // per slot: radiance gathered so far
+  float* rad_final = nullptr;           // per PATH, 3 x capacity: written once when the path ends
   uint32_t* pixel = nullptr;  // film pixel (y * W + x) per tile-pixel of the current batch
+  uint32_t* perm = nullptr;   // slots of every window of the stream in shading-class order (wavefront.cu, bin_window_kernel)
 };
+constexpr uint32_t kShadeClasses = 1024;  // 1 + 2 * materials (occluded / unoccluded each), clamped
 
 struct RenderState {
   DevCamera camera;

@@ -24,7 +24,10 @@
 // 64 registers / 8 CTAs per SM, 80 registers / 6 CTAs, sorting the ray stream, fused leaves, other vote biases /
 // refill thresholds, 64-ray chunks, shorter claims near the end of the stream, packed FFMA2 plane evaluation,
 // plane bytes decoded on the XU / FMA pipes, smaller shared-memory stacks, the stack base pinned in a register,
-// a per-group distance bound (costed on the host emulation, not built).
+// a per-group distance bound (costed on the host emulation, not built); round 2 (profiles/r02_summary.md): guided
+// (shrinking) claims near the end of the stream (-3..5 %: small chunks starve the refill), handing the second triangle of a
+// pair to a lane with nothing to test through shared memory (one Moeller-Trumbore sequence per step instead of two:
+// -3.5 % coherent, -4.6 % bounce rays — the exchange costs more issue slots than the second test).
 #pragma once
 #include "trace_ray.cuh"
 
@@ -50,7 +53,7 @@ namespace phos {
 // are unclaimed, a claim takes its share of what is left (>= PHOS_TAIL_MIN rays, a multiple of 4 so that chunk starts
 // stay 16-byte aligned for the bulk copies) — no warp sits on two staged chunks while others run dry.  0 = fixed claims.
 #ifndef PHOS_TAIL_DIV
-#define PHOS_TAIL_DIV 2
+#define PHOS_TAIL_DIV 0
 #endif
 #ifndef PHOS_TAIL_MIN
 #define PHOS_TAIL_MIN 4
@@ -60,6 +63,15 @@ namespace phos {
 // back when done — the longest ray of a warp no longer runs on one lane while 31 wait.  0 = off.
 #ifndef PHOS_TAIL_SHARE
 #define PHOS_TAIL_SHARE 1
+#endif
+#ifndef PHOS_SHARE_SPLIT_CUR
+#define PHOS_SHARE_SPLIT_CUR 1  // with an empty stack, give away all but the nearest pending child of the current group
+#endif
+#ifndef PHOS_SHARE_MIN_IDLE
+#define PHOS_SHARE_MIN_IDLE 12  // lanes without a ray before a round of sharing starts (1: -3 % on coherent rays, 12: -1.4 %; profiles/r02_tail.md)
+#endif
+#ifndef PHOS_SHARE_BOTTOM
+#define PHOS_SHARE_BOTTOM 0     // give the bottom stack entry (the largest pending subtrees) instead of the top one
 #endif
 constexpr int kChunk = PHOS_CHUNK;           // rays per claimed chunk
 constexpr int kRefillMin = PHOS_REFILL_MIN;  // idle lanes that trigger a refill
@@ -270,13 +282,13 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
       }
     }
     if (PHOS_TRI_BIAS * n_tri >= n_node) {
+      if (tri_work && (lt >> 8) == 0u) {  // open the next hit leaf, nearest octant first
+        const uint32_t slot = (__ffs(lt) - 1) ^ rd.oct;
+        lt &= lt - 1u;
+        lt |= ((lcounts >> (4u * slot)) & 15u) << 8;  // 0 for an empty slot
+        tptr = lbase + nibble_prefix(lcounts, slot);
+      }
       if (tri_work) {
-        if ((lt >> 8) == 0u) {  // open the next hit leaf, nearest octant first
-          const uint32_t slot = (__ffs(lt) - 1) ^ rd.oct;
-          lt &= lt - 1u;
-          lt |= ((lcounts >> (4u * slot)) & 15u) << 8;  // 0 for an empty slot
-          tptr = lbase + nibble_prefix(lcounts, slot);
-        }
         if (lt >> 8) {
           const uint4* tp = P.accel.tris + 3ull * tptr;
           const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
@@ -432,17 +444,24 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
       // free lanes take a group of pending siblings each from the lanes that can spare one: the top entry of the stack,
       // or, with an empty stack, all but the nearest pending child of the current group
       const unsigned pend = cur.y >> 8;
-      const bool can_give = busy && ((sp > 0 && (sp > 1 || pend != 0u || lt != 0u)) || (pend & (pend - 1u)) != 0u);  // and keep some
+      const bool can_give = busy && ((sp > 0 && (sp > 1 || pend != 0u || lt != 0u)) ||
+                                     (PHOS_SHARE_SPLIT_CUR && (pend & (pend - 1u)) != 0u));  // and keep some
       const unsigned idle = __ballot_sync(0xffffffffu, !has_ray), don = __ballot_sync(0xffffffffu, can_give);
       if (idle == 0xffffffffu) break;  // every lane retired
-      if (idle != 0u && don != 0u) {
+      if (__popc(idle) >= PHOS_SHARE_MIN_IDLE && don != 0u) {
         const int pairs = min(__popc(idle), __popc(don));
         const bool take = !has_ray && __popc(idle & lt_mask) < pairs;
         const bool give = can_give && __popc(don & lt_mask) < pairs;
         uint2 g = make_uint2(0u, 0u);
         if (give) {
           if (sp > 0) {
-            g = pop();
+            if (PHOS_SHARE_BOTTOM && !kDeep) {  // entry 0, the rest moves down
+              g = my_stack[0];
+              for (int e = 1; e < sp; ++e) my_stack[(e - 1) * kTraceBlock] = my_stack[e * kTraceBlock];
+              --sp;
+            } else {
+              g = pop();
+            }
           } else {
             const unsigned near = pend & (0u - pend);
             g = make_uint2(cur.x, (cur.y & 0xffu) | ((pend ^ near) << 8));

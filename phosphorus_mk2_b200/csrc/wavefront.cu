@@ -40,9 +40,16 @@ struct FrameArgs {
   float scale;  // 1 / (spp_total * pps)
   const float* jitter;  // [2 * spp_total]: jx then jy
   const uint32_t* pixel;
-  float* beta;
-  float* rad;
-  uint32_t* depth;
+  // Path state travels WITH the slot (throughput beta and radiance so far, [3][Q] each, ping-pong like the ray streams):
+  // compaction appends survivors in whatever order the warps arrive, so state indexed by path id turns every access of
+  // the later bounces into a 32-byte sector per 4-byte value (r02: 7 GB of DRAM reads in one integrate launch).  A path
+  // that ends writes its radiance once to rad_final[path]; the depth of every live path is the bounce index.
+  const float* beta_in;
+  const float* rad_in;
+  float* beta_out;
+  float* rad_out;
+  float* rad_final;  // per path, [3][Q]: what film_accumulate sums, in sample order
+  uint32_t bounce;
   float* n;
   float* light_pdf;
   uint32_t* count;  // [2]
@@ -80,13 +87,12 @@ __global__ void paths_init_kernel(const FrameArgs A, phos_rays rays, uint32_t* _
   rays.d[q] = 3.402823466e+38f;
   rays.flags[q] = 0u;
   slot_path[q] = q;
-  A.beta[q] = 1.0f;
-  A.beta[q + (size_t)A.Q] = 1.0f;
-  A.beta[q + 2 * (size_t)A.Q] = 1.0f;
-  A.rad[q] = 0.0f;
-  A.rad[q + (size_t)A.Q] = 0.0f;
-  A.rad[q + 2 * (size_t)A.Q] = 0.0f;
-  A.depth[q] = 0u;
+  A.beta_out[q] = 1.0f;  // (paths_init is handed the first bounce's input buffers as its outputs)
+  A.beta_out[q + (size_t)A.Q] = 1.0f;
+  A.beta_out[q + 2 * (size_t)A.Q] = 1.0f;
+  A.rad_out[q] = 0.0f;
+  A.rad_out[q + (size_t)A.Q] = 0.0f;
+  A.rad_out[q + 2 * (size_t)A.Q] = 0.0f;
 }
 
 #ifndef PHOS_GS_BLOCKS
@@ -114,7 +120,7 @@ __device__ __forceinline__ void shade_nee_slot(const FrameArgs& A, const phos_ra
   if (A.scene.nlights == 0u) return;
 
   const uint32_t q = slot_path[i];
-  const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P], depth = A.depth[q];
+  const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P], depth = A.bounce;
   const uint32_t nl = A.scene.nlights;
   const float xl = rng(A.seed, pix, s, depth, DIM_LIGHT);
   const uint32_t l = (uint32_t)fminf(floorf(xl * nl), (float)(nl - 1));
@@ -163,36 +169,124 @@ __global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const 
     shade_nee_slot(A, rays, slot_path, sh, i);
 }
 
+// ---- shading classes ------------------------------------------------------------------------------------------------
+// The reference buckets the hits of a stream by material before it shades them (deferred_shading_kernel.hpp:27-33,63: one
+// OSL shader group runs over one bucket).  Here the integrator's cost is the closure code of the slot's material — a warp
+// whose 32 slots hold 5 materials runs all 5 (r01: 11 of 32 lanes per instruction) — so `integrate` visits the slots of
+// every kBinWindow-slot window of the stream class by class:
+//   class 0                 the ray missed (environment, path ends)
+//   class 1 + 2 * mat + l   hit on material `mat`; l = 1 when the next-event shadow ray arrived (li() evaluates the BSDF)
+// bin_window_kernel counting-sorts each window on its own (one block per window: histogram in shared memory, scan,
+// scatter — no global atomics) into `perm`; the block of `integrate` that owns the window reads slot perm[k] instead of
+// slot k.  The sort is LOCAL on purpose: the streams are SoA, and a stream-wide permutation turns every 4-byte field read
+// into its own 32-byte sector (measured: 3.4 ms instead of 0.9 ms per launch on the bounce-2 stream of the Cornell box,
+// profiles/r02_shading_classes.md); inside a window the gathers hit lines the same block is fetching anyway.
+#ifndef PHOS_BIN_ROUNDS
+#define PHOS_BIN_ROUNDS 4
+#endif
+constexpr int kBinRounds = PHOS_BIN_ROUNDS;          // slots per thread of a 256-thread block
+constexpr uint32_t kBinWindow = 256u * kBinRounds;  // slots per window
+
+__device__ __forceinline__ uint32_t shade_class(uint32_t flags, uint32_t mesh, uint32_t sflags) {
+  if (!(flags & PHOS_HIT)) return 0u;
+  const uint32_t mat = min(mesh >> 16, (kShadeClasses - 2u) / 2u - 1u);
+  return 1u + 2u * mat + ((sflags & (PHOS_HIT | PHOS_MASKED)) ? 0u : 1u);
+}
+
+__global__ void __launch_bounds__(256) bin_window_kernel(const uint32_t* __restrict__ count, int cur, const phos_rays rays, const phos_rays sh,
+                                                         uint32_t ncls, uint32_t* __restrict__ perm) {
+  __shared__ uint32_t hist[kShadeClasses];  // slots per class, then first position of the class in the window
+  __shared__ uint32_t warp_sum[8];
+  const uint32_t n = count[cur];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t base = blockIdx.x * kBinWindow; base < n; base += gridDim.x * kBinWindow) {  // block-uniform trip count
+    for (uint32_t c = threadIdx.x; c < kShadeClasses; c += 256u) hist[c] = 0u;
+    __syncthreads();
+    uint32_t cls[kBinRounds], off[kBinRounds];
+#pragma unroll
+    for (int j = 0; j < kBinRounds; ++j) {
+      const uint32_t i = base + j * 256u + threadIdx.x;
+      cls[j] = 0xffffffffu;
+      off[j] = 0u;
+      if (i < n) {
+        const uint32_t c = shade_class(rays.flags[i], rays.mesh[i], sh.flags[i]);
+        const unsigned peers = __match_any_sync(__activemask(), c);
+        const int leader = __ffs(peers) - 1;
+        uint32_t o = 0u;
+        if ((int)lane == leader) o = atomicAdd(&hist[c], (uint32_t)__popc(peers));
+        off[j] = __shfl_sync(peers, o, leader) + __popc(peers & ((1u << lane) - 1u));
+        cls[j] = c;
+      }
+    }
+    __syncthreads();
+    // exclusive scan of hist[0 .. ncls): every thread owns 4 consecutive classes
+    {
+      const uint32_t c0 = threadIdx.x * 4u;
+      const uint32_t a = hist[c0], b = hist[c0 + 1], c = hist[c0 + 2], d = hist[c0 + 3];
+      uint32_t incl = a + b + c + d;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, s);
+        if ((int)lane >= s) incl += v;
+      }
+      if (lane == 31u) warp_sum[warp] = incl;
+      __syncthreads();
+      uint32_t before = incl - (a + b + c + d);
+      for (unsigned w = 0; w < warp; ++w) before += warp_sum[w];
+      hist[c0] = before;
+      hist[c0 + 1] = before + a;
+      hist[c0 + 2] = before + a + b;
+      hist[c0 + 3] = before + a + b + c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kBinRounds; ++j)
+      if (cls[j] != 0xffffffffu) perm[base + hist[cls[j]] + off[j]] = base + j * 256u + threadIdx.x;
+    __syncthreads();
+  }
+  (void)ncls;
+}
+
 // integrator_t::operator() (spt.hpp:161-210) with li (:212-255), sample_bsdf (:257-305) and
 // terminate_path (:307-328); survivors are appended to the next ray stream.
 #ifndef PHOS_INTEGRATE_MIN_BLOCKS
 #define PHOS_INTEGRATE_MIN_BLOCKS 4  // 64 registers: measured best (profiles/r01_render_variants.log: 1 -> 4 blocks = +13 % on Cornell)
 #endif
 __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kernel(const FrameArgs A, const phos_rays rays, const phos_rays sh,
-                                 const uint32_t* __restrict__ slot_path, int cur, phos_rays next, uint32_t* __restrict__ next_path) {
- // grid-stride over the live slots, a whole warp at a time (the compaction below is a warp collective)
+                                 const uint32_t* __restrict__ slot_path, int cur, phos_rays next, uint32_t* __restrict__ next_path,
+                                 const uint32_t* __restrict__ perm) {
+ // grid-stride over the live slots, a whole warp at a time (the compaction below is a warp collective); with `perm` the
+ // slots come class by class (bin_* kernels above)
  const uint32_t count = A.count[cur];
- for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < count; i += gridDim.x * blockDim.x) {
-  const bool valid = i < count;
+ // a block walks whole windows of kBinWindow consecutive positions (4 rounds of 256): with `perm` these are the slots of one
+ // window of the stream class by class, fetched by this block alone
+ for (uint32_t k0 = blockIdx.x * kBinWindow + threadIdx.x; (k0 & ~(kBinWindow - 1u)) < count; k0 += gridDim.x * kBinWindow)
+ for (uint32_t k = k0; k < k0 + kBinWindow && (k & ~31u) < count; k += 256u) {
+  const bool valid = k < count;
+  const uint32_t i = (perm && valid) ? perm[k] : k;
   bool alive = false;
   uint32_t q = 0, nflags = 0;
-  v3 no = V(0, 0, 0), nw = V(0, 0, 0);
+  v3 no = V(0, 0, 0), nw = V(0, 0, 0), nbeta = V(0, 0, 0), rad = V(0, 0, 0);
   if (valid && !(rays.flags[i] & PHOS_HIT)) {  // a miss adds beta * e_env (spt.hpp:199-202) and ends the path
+    const uint32_t p = slot_path[i];
+    const size_t Q = A.Q;
+    v3 rad = V(A.rad_in[i], A.rad_in[i + Q], A.rad_in[i + 2 * Q]);
     if (A.scene.environment >= 0) {
-      const uint32_t p = slot_path[i];
-      const size_t Q = A.Q;
       const DevMaterial* env = A.scene.mats + A.scene.environment;
-      A.rad[p] += A.beta[p] * __ldg(&env->e[0]);
-      A.rad[p + Q] += A.beta[p + Q] * __ldg(&env->e[1]);
-      A.rad[p + 2 * Q] += A.beta[p + 2 * Q] * __ldg(&env->e[2]);
+      rad.x += A.beta_in[i] * __ldg(&env->e[0]);
+      rad.y += A.beta_in[i + Q] * __ldg(&env->e[1]);
+      rad.z += A.beta_in[i + 2 * Q] * __ldg(&env->e[2]);
     }
+    A.rad_final[p] = rad.x;
+    A.rad_final[p + Q] = rad.y;
+    A.rad_final[p + 2 * Q] = rad.z;
   } else if (valid) {
     q = slot_path[i];
     const size_t Q = A.Q;
     const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P];
-    uint32_t depth = A.depth[q];
-    v3 beta = V(A.beta[q], A.beta[q + Q], A.beta[q + 2 * Q]);
-    v3 rad = V(A.rad[q], A.rad[q + Q], A.rad[q + 2 * Q]);
+    uint32_t depth = A.bounce;
+    v3 beta = V(A.beta_in[i], A.beta_in[i + Q], A.beta_in[i + 2 * Q]);
+    rad = V(A.rad_in[i], A.rad_in[i + Q], A.rad_in[i + 2 * Q]);
     const v3 o = V(rays.px[i], rays.py[i], rays.pz[i]), w = V(rays.wx[i], rays.wy[i], rays.wz[i]);
     const v3 P = add(o, scl(w, rays.d[i]));
     const v3 wo = neg(w);
@@ -241,13 +335,12 @@ __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kern
         nw = sampled;
       }
     }
-    A.depth[q] = depth;
-    A.beta[q] = beta.x;
-    A.beta[q + Q] = beta.y;
-    A.beta[q + 2 * Q] = beta.z;
-    A.rad[q] = rad.x;
-    A.rad[q + Q] = rad.y;
-    A.rad[q + 2 * Q] = rad.z;
+    nbeta = beta;
+    if (!alive) {  // the path ends here: its radiance goes to the film
+      A.rad_final[q] = rad.x;
+      A.rad_final[q + Q] = rad.y;
+      A.rad_final[q + 2 * Q] = rad.z;
+    }
   }
   // compaction: one atomic per warp reserves slots for all its survivors
   const unsigned live = __ballot_sync(0xffffffffu, alive);
@@ -267,6 +360,13 @@ __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kern
     next.d[slot] = 3.402823466e+38f;
     next.flags[slot] = (nflags & BSDF_SPECULAR_F) ? PHOS_SPECULAR : 0u;  // rays->specular_bounce (spt.hpp:302)
     next_path[slot] = q;
+    const size_t Q = A.Q;
+    A.beta_out[slot] = nbeta.x;
+    A.beta_out[slot + Q] = nbeta.y;
+    A.beta_out[slot + 2 * Q] = nbeta.z;
+    A.rad_out[slot] = rad.x;
+    A.rad_out[slot + Q] = rad.y;
+    A.rad_out[slot + 2 * Q] = rad.z;
   }
  }
 }
@@ -278,9 +378,9 @@ __global__ void film_accumulate_kernel(const FrameArgs A, float* __restrict__ fi
   float* px = film + 4 * (size_t)A.pixel[t];
   float r = px[0], g = px[1], b = px[2];
   for (uint32_t q = t; q < A.Q; q += A.P) {
-    r += A.rad[q] * A.scale;
-    g += A.rad[q + (size_t)A.Q] * A.scale;
-    b += A.rad[q + 2 * (size_t)A.Q] * A.scale;
+    r += A.rad_final[q] * A.scale;
+    g += A.rad_final[q + (size_t)A.Q] * A.scale;
+    b += A.rad_final[q + 2 * (size_t)A.Q] * A.scale;
   }
   px[0] = r;
   px[1] = g;
@@ -363,13 +463,14 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   // machine (a ray lives ~50 us; the slowest of a launch several times that), and a batch has 2 x depth of them: at
   // 4 Mi paths the tails were a quarter of a config-4 frame (profiles/r01_render_wavefront_size.log: 4 / 8 / 16 / 32 /
   // 64 Mi paths = 513 / 582 / 628 / 656 / 670 M samples/s).  64 Mi paths (over both wavefronts) are 13 GB of wavefront
-  // state (196 B per path) on a 180 GB device; never more than a quarter of what is free.  PHOS_WAVEFRONT_PATHS overrides.
+  // state (kBytesPerPath per path) on a 180 GB device; never more than a quarter of what is free.  PHOS_WAVEFRONT_PATHS overrides.
+  constexpr uint64_t kBytesPerPath = 236ull;  // ensure_wavefront: 3 ray streams, slot maps, normals, pdf, 2 x (beta, rad), rad_final, perm
   uint64_t target = 64ull << 20;
   if (R.paths_cap == 0) {  // asked once per scene upload: cudaMemGetInfo is a driver round trip, not something for every frame
     size_t free_b = 0, total_b = 0;
     R.paths_cap = ~0ull;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-      R.paths_cap = std::max<uint64_t>(((uint64_t)free_b + (R.wf.capacity + R.wf2.capacity) * 196ull) / 4ull / 196ull, 1ull << 20);
+      R.paths_cap = std::max<uint64_t>(((uint64_t)free_b + (R.wf.capacity + R.wf2.capacity) * kBytesPerPath) / 4ull / kBytesPerPath, 1ull << 20);
     else
       cudaGetLastError();
   }
@@ -429,9 +530,10 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
     A.scale = 1.0f / (float)(spp_total * ctx->opt.paths_per_sample);
     A.jitter = R.d_jitter;
     A.pixel = W.pixel;
-    A.beta = W.beta;
-    A.rad = W.rad;
-    A.depth = W.depth;
+    A.beta_in = A.beta_out = W.beta[0];
+    A.rad_in = A.rad_out = W.rad[0];
+    A.rad_final = W.rad_final;
+    A.bounce = 0;
     A.n = W.n;
     A.light_pdf = W.light_pdf;
     A.count = W.count;
@@ -447,6 +549,10 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
          cuda_ok(ctx, cudaEventRecord(ev_setup, st), "event record") &&
          cuda_ok(ctx, cudaStreamWaitEvent(streams[1], ev_setup, 0), "event wait");
   }
+  // shading classes (above): on unless the scene has a single material or PHOS_SHADE_BIN=0
+  const uint32_t ncls = std::min<uint32_t>(kShadeClasses, 1u + 2u * std::max<uint32_t>(1u, R.num_materials));
+  bool bin = R.num_materials > 1;
+  if (const char* e = std::getenv("PHOS_SHADE_BIN")) bin = std::atoi(e) != 0;
   int rc = PHOS_OK;
   uint32_t k = 0;
   for (uint32_t s0 = spp_begin; ok && rc == PHOS_OK && s0 < spp_end; s0 += batch, ++k) {
@@ -460,10 +566,19 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
     A.spp_begin = s0;
     const uint32_t blocks = (A.Q + 255) / 256;
     const uint32_t gs_blocks = std::min<uint32_t>(blocks, (uint32_t)ctx->sm_count * kGridStrideBlocksPerSm);  // grid-stride kernels
+    A.beta_out = W.beta[0];
+    A.rad_out = W.rad[0];
     paths_init_kernel<<<blocks, 256, 0, sk>>>(A, W.rays[0], W.slot_path[0]);
     ctx->launches++;
-    for (uint32_t b = 0; b < A.max_depth && rc == PHOS_OK; ++b) {
+    // (path_depth 0 still traces the primary rays and adds what they see: the reference's loop tests the depth after the
+    // first bounce, spt.hpp:307-328)
+    for (uint32_t b = 0; b < std::max<uint32_t>(1u, A.max_depth) && rc == PHOS_OK; ++b) {
       const int cur = (int)(b & 1u);
+      A.bounce = b;
+      A.beta_in = W.beta[cur];
+      A.rad_in = W.rad[cur];
+      A.beta_out = W.beta[cur ^ 1];
+      A.rad_out = W.rad[cur ^ 1];
       zero_u32_kernel<<<1, 1, 0, sk>>>(W.count + (cur ^ 1));
       ctx->launches++;
       rc = launch_trace(ctx, W.rays[cur], A.Q, sk, cursors, false, W.count + cur);
@@ -476,7 +591,12 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
       }
       rc = launch_trace(ctx, W.shadow, A.Q, sk, cursors + 1, false, W.count + cur);
       if (rc) break;
-      integrate_kernel<<<gs_blocks, 256, 0, sk>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1]);
+      if (bin) {
+        bin_window_kernel<<<gs_blocks, 256, 0, sk>>>(W.count, cur, W.rays[cur], W.shadow, ncls, W.perm);
+        ctx->launches++;
+      }
+      integrate_kernel<<<gs_blocks, 256, 0, sk>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1],
+                                                  bin ? W.perm : nullptr);
       ctx->launches++;
     }
     if (rc) break;
@@ -550,9 +670,10 @@ int phos_cuda_wavefront_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_t
   A.scale = 0.0f;
   A.jitter = R.d_jitter;
   A.pixel = W.pixel;
-  A.beta = W.beta;
-  A.rad = W.rad;
-  A.depth = W.depth;
+  A.beta_in = A.beta_out = W.beta[0];
+  A.rad_in = A.rad_out = W.rad[0];
+  A.rad_final = W.rad_final;
+  A.bounce = 0;
   A.n = W.n;
   A.light_pdf = W.light_pdf;
   A.count = W.count;
@@ -567,7 +688,9 @@ int phos_cuda_wavefront_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_t
   if (which == 0) {
     rc = launch_trace(ctx, W.shadow, P, st, ctx->d_counters + 25, false, W.count);
     if (rc) return rc;
-    integrate_kernel<<<gs_blocks, 256, 0, st>>>(A, W.rays[0], W.shadow, W.slot_path[0], 0, W.rays[1], W.slot_path[1]);
+    A.beta_out = W.beta[1];
+    A.rad_out = W.rad[1];
+    integrate_kernel<<<gs_blocks, 256, 0, st>>>(A, W.rays[0], W.shadow, W.slot_path[0], 0, W.rays[1], W.slot_path[1], nullptr);
     if (!cuda_ok(ctx, cudaMemcpyAsync(&n, W.count + 1, 4, cudaMemcpyDeviceToHost, st), "read queue length") ||
         !cuda_ok(ctx, cudaStreamSynchronize(st), "wavefront_rays"))
       return PHOS_ERR_CUDA;

@@ -41,21 +41,31 @@ def test_reference_host_code_drives_the_cuda_device(reflib_cuda, oracle):
 def test_gpu_and_cpu_device_agree_statistically(reflib_cuda):
     reflib = reflib_cuda
     """cuda_t next to cpu_t behind the same interface.  The device normalises through the host's RCPSS like the
-    reference (phos_cuda_reference_normalize, on in cuda_t::make), so the two images agree within Monte-Carlo noise —
-    a frame shared by both devices does not checkerboard; with PHOS_EXACT_NORMALIZE=1 the GPU image is the brighter
-    one of exact arithmetic (the reference's shadow rays overshoot, DESIGN.md §4)."""
-    sc = scenes.cornell_box(48, 48)
-    gpu, _ = reflib.scene(sc).render_cuda(spp=1024, pps=1, depth=4)
-    cpu, _ = reflib.scene(sc).render(1024, 1, 4, single_threaded=False)
-    for stat in (np.median, np.mean):
-        g, c = stat(np.clip(gpu[..., :3], 0, 4)), stat(np.clip(cpu[..., :3], 0, 4))
-        assert abs(g / c - 1.0) < 0.02, (stat.__name__, g, c)
+    reference (phos_cuda_reference_normalize, on in cuda_t::make): the 13-40 % gap between exact arithmetic and the
+    reference's images (its shadow rays overshoot into the light, DESIGN.md §4) closes to 2-4 %.  What is left is the other
+    half of the same artefact: an overshooting shadow ray counts as occluded only if the reference's approximate slab test
+    also finds the light's own (flat) leaf box, which it misses for a share of them; the device's traversal is exact by
+    contract (every hit Moeller-Trumbore accepts is found), so it is the darker of the two by those rays.  The oracle's
+    rcp_mode 1 (RCPSS + the reference's slab test) agrees with cpu_t to 1 % (tests/test_oracle_render.py), rcp_mode 2
+    (RCPSS + exact traversal) is this device to 1e-3 (tests/test_gpu_render.py)."""
+    # (lights 40 cm below the ceiling: without the 1 / d^2 spikes of next-event estimation onto the ceiling right above
+    # them plain means converge — see tests/test_oracle_render.py::test_oracle_converges_to_the_reference_renderer)
+    sc = scenes.cornell_box(32, 32, light_y=1.6)
+    gpu, _ = reflib.scene(sc).render_cuda(spp=4096, pps=1, depth=4)
+    cpu, _ = reflib.scene(sc).render(4096, 1, 4, single_threaded=False)
+
+    def stats(img):
+        img = img[..., :3]
+        h, w = img.shape[:2]
+        return np.array([img.mean(), img[:h // 2].mean(), img[h // 2:].mean(), img[:, :w // 2].mean(), img[:, w // 2:].mean(), np.median(img)])
+    g, c = stats(gpu), stats(cpu)
+    assert np.all((g / c > 0.94) & (g / c < 1.005)), (g, c)
     os.environ["PHOS_EXACT_NORMALIZE"] = "1"
     try:
         exact, _ = reflib.scene(sc).render_cuda(spp=256, pps=1, depth=4)
     finally:
         del os.environ["PHOS_EXACT_NORMALIZE"]
-    assert 1.05 < np.median(exact[..., :3]) / np.median(cpu[..., :3]) < 1.6
+    assert 1.05 < exact[..., :3].mean() / cpu[..., :3].mean() < 1.6
 
 
 def test_discover_returns_one_cuda_device_per_gpu(reflib_cuda):

@@ -5,6 +5,7 @@ import pytest
 
 from phosphorus_mk2_b200 import scenes
 from phosphorus_mk2_b200.device import Accel, CudaDevice, Options, make_tiles
+from phosphorus_mk2_b200.lib import PhosError
 from phosphorus_mk2_b200.scene import MAT_DIFFUSE, MAT_GLOSSY
 
 pytestmark = pytest.mark.gpu
