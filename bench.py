@@ -271,6 +271,7 @@ def issue_figures(run: Run, workload: str, prof: dict, ms: float):
             "lanes_per_instruction": lanes,
             "lanes_per_node_step": prof["lanes_node_steps"] / max(prof["warp_node_steps"], 1),
             "lanes_per_tri_step": prof["lanes_tri_steps"] / max(prof["warp_tri_steps"], 1),
+            "step_counters": prof,
             "issue_source": "in-run warp-step counters x instruction weights of profiles/ncu_capture.json; "
                             f"{run.sm_count} SMs x 4 schedulers x {run.sm_mhz:.0f} MHz",
             "ncu_capture": run.capture.get(workload)}

@@ -174,8 +174,9 @@ __global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const 
 // OSL shader group runs over one bucket).  Here the integrator's cost is the closure code of the slot's material — a warp
 // whose 32 slots hold 5 materials runs all 5 (r01: 11 of 32 lanes per instruction) — so `integrate` visits the slots of
 // every kBinWindow-slot window of the stream class by class:
-//   class 0                 the ray missed (environment, path ends)
-//   class 1 + 2 * mat + l   hit on material `mat`; l = 1 when the next-event shadow ray arrived (li() evaluates the BSDF)
+//   class 0                          the ray missed (environment, path ends)
+//   class 1 + 4 * mat + 2 * l + a    hit on material `mat`; l = 1 when the next-event shadow ray arrived (li() evaluates the
+//                                    BSDF), a = 1 when the path survives Russian roulette (bsdf_t::sample runs)
 // bin_window_kernel counting-sorts each window on its own (one block per window: histogram in shared memory, scan,
 // scatter — no global atomics) into `perm`; the block of `integrate` that owns the window reads slot perm[k] instead of
 // slot k.  The sort is LOCAL on purpose: the streams are SoA, and a stream-wide permutation turns every 4-byte field read
@@ -187,17 +188,35 @@ __global__ void shade_nee_kernel(const FrameArgs A, const phos_rays rays, const 
 constexpr int kBinRounds = PHOS_BIN_ROUNDS;          // slots per thread of a 256-thread block
 constexpr uint32_t kBinWindow = 256u * kBinRounds;  // slots per window
 
-__device__ __forceinline__ uint32_t shade_class(uint32_t flags, uint32_t mesh, uint32_t sflags) {
-  if (!(flags & PHOS_HIT)) return 0u;
-  const uint32_t mat = min(mesh >> 16, (kShadeClasses - 2u) / 2u - 1u);
-  return 1u + 2u * mat + ((sflags & (PHOS_HIT | PHOS_MASKED)) ? 0u : 1u);
+#ifndef PHOS_CLASS_ALIVE
+#define PHOS_CLASS_ALIVE 1
+#endif
+__device__ __forceinline__ uint32_t shade_class(const FrameArgs& A, const phos_rays& rays, const phos_rays& sh,
+                                                const uint32_t* __restrict__ slot_path, uint32_t i) {
+  if (!(rays.flags[i] & PHOS_HIT)) return 0u;
+  const uint32_t mat = min(rays.mesh[i] >> 16, (kShadeClasses - 4u) / 4u - 1u);
+  const uint32_t lit = (sh.flags[i] & (PHOS_HIT | PHOS_MASKED)) ? 0u : 1u;
+  uint32_t alive = 1u;
+#if PHOS_CLASS_ALIVE
+  // terminate_path as integrate_kernel decides it (only the grouping depends on this copy, not the image)
+  const uint32_t depth = A.bounce + 1u;
+  if (depth >= A.max_depth) {
+    alive = 0u;
+  } else if (depth >= 3u) {
+    const size_t Q = A.Q;
+    const uint32_t q = slot_path[i];
+    const float yb = 0.212671f * A.beta_in[i] + 0.715160f * A.beta_in[i + Q] + 0.072169f * A.beta_in[i + 2 * Q];
+    alive = rng(A.seed, A.pixel[q % A.P], A.spp_begin + q / A.P, depth - 1u, DIM_RR) >= fmaxf(0.05f, 1.0f - yb) ? 1u : 0u;
+  }
+#endif
+  return 1u + 4u * mat + 2u * lit + alive;
 }
 
-__global__ void __launch_bounds__(256) bin_window_kernel(const uint32_t* __restrict__ count, int cur, const phos_rays rays, const phos_rays sh,
-                                                         uint32_t ncls, uint32_t* __restrict__ perm) {
+__global__ void __launch_bounds__(256) bin_window_kernel(const FrameArgs A, int cur, const phos_rays rays, const phos_rays sh,
+                                                         const uint32_t* __restrict__ slot_path, uint32_t* __restrict__ perm) {
   __shared__ uint32_t hist[kShadeClasses];  // slots per class, then first position of the class in the window
   __shared__ uint32_t warp_sum[8];
-  const uint32_t n = count[cur];
+  const uint32_t n = A.count[cur];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint32_t base = blockIdx.x * kBinWindow; base < n; base += gridDim.x * kBinWindow) {  // block-uniform trip count
     for (uint32_t c = threadIdx.x; c < kShadeClasses; c += 256u) hist[c] = 0u;
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(256) bin_window_kernel(const uint32_t* __restr
       cls[j] = 0xffffffffu;
       off[j] = 0u;
       if (i < n) {
-        const uint32_t c = shade_class(rays.flags[i], rays.mesh[i], sh.flags[i]);
+        const uint32_t c = shade_class(A, rays, sh, slot_path, i);
         const unsigned peers = __match_any_sync(__activemask(), c);
         const int leader = __ffs(peers) - 1;
         uint32_t o = 0u;
@@ -244,7 +263,6 @@ __global__ void __launch_bounds__(256) bin_window_kernel(const uint32_t* __restr
       if (cls[j] != 0xffffffffu) perm[base + hist[cls[j]] + off[j]] = base + j * 256u + threadIdx.x;
     __syncthreads();
   }
-  (void)ncls;
 }
 
 // integrator_t::operator() (spt.hpp:161-210) with li (:212-255), sample_bsdf (:257-305) and
@@ -550,7 +568,6 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
          cuda_ok(ctx, cudaStreamWaitEvent(streams[1], ev_setup, 0), "event wait");
   }
   // shading classes (above): on unless the scene has a single material or PHOS_SHADE_BIN=0
-  const uint32_t ncls = std::min<uint32_t>(kShadeClasses, 1u + 2u * std::max<uint32_t>(1u, R.num_materials));
   bool bin = R.num_materials > 1;
   if (const char* e = std::getenv("PHOS_SHADE_BIN")) bin = std::atoi(e) != 0;
   int rc = PHOS_OK;
@@ -592,7 +609,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
       rc = launch_trace(ctx, W.shadow, A.Q, sk, cursors + 1, false, W.count + cur);
       if (rc) break;
       if (bin) {
-        bin_window_kernel<<<gs_blocks, 256, 0, sk>>>(W.count, cur, W.rays[cur], W.shadow, ncls, W.perm);
+        bin_window_kernel<<<gs_blocks, 256, 0, sk>>>(A, cur, W.rays[cur], W.shadow, W.slot_path[cur], W.perm);
         ctx->launches++;
       }
       integrate_kernel<<<gs_blocks, 256, 0, sk>>>(A, W.rays[cur], W.shadow, W.slot_path[cur], cur, W.rays[cur ^ 1], W.slot_path[cur ^ 1],
