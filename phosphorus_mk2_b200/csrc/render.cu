@@ -326,7 +326,7 @@ static void release_one(Wavefront& wf) {
   free_rays(wf.rays[0]);
   free_rays(wf.rays[1]);
   free_rays(wf.shadow);
-  void* ptrs[] = {wf.slot_path[0], wf.slot_path[1], wf.count, wf.n, wf.light_pdf, wf.beta[0], wf.beta[1], wf.rad[0], wf.rad[1], wf.rad_final, wf.pixel, wf.perm};
+  void* ptrs[] = {wf.slot_path[0], wf.slot_path[1], wf.count, wf.n, wf.lightw, wf.beta[0], wf.beta[1], wf.rad[0], wf.rad[1], wf.rad_final, wf.pixel, wf.perm};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   wf = Wavefront();
@@ -345,7 +345,7 @@ bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixel
     get((void**)&wf.slot_path[1], cap * 4);
     get((void**)&wf.count, 16);
     get((void**)&wf.n, cap * 12);
-    get((void**)&wf.light_pdf, cap * 4);
+    get((void**)&wf.lightw, cap * 16);
     for (int k = 0; k < 2; ++k) {
       get((void**)&wf.beta[k], cap * 12);
       get((void**)&wf.rad[k], cap * 12);

@@ -24,7 +24,7 @@ struct Wavefront {
   uint32_t* slot_path[2] = {nullptr, nullptr};  // slot -> path, ping-pong
   uint32_t* count = nullptr;  // [0..1] live slots of stream 0 / 1 (device counters), [2] scratch
   float* n = nullptr;         // shading normal per slot, 3 x capacity
-  float* light_pdf = nullptr; // per slot
+  float* lightw = nullptr;    // per slot, 4 x capacity: light side of the next-event estimate
   float* beta[2] = {nullptr, nullptr};  // per SLOT, 3 x capacity, ping-pong with the ray streams (wavefront.cu FrameArgs)
   float* rad[2] = {nullptr, nullptr};   // per slot: radiance gathered so far
   float* rad_final = nullptr;           // per PATH, 3 x capacity: written once when the path ends

@@ -70,6 +70,15 @@ namespace phos {
 #ifndef PHOS_SHARE_MIN_IDLE
 #define PHOS_SHARE_MIN_IDLE 12  // lanes without a ray before a round of sharing starts (1: -3 % on coherent rays, 12: -1.4 %; profiles/r02_tail.md)
 #endif
+#ifndef PHOS_SHARE_COHERENCE_TEST
+#define PHOS_SHARE_COHERENCE_TEST 1
+#endif
+#ifndef PHOS_SHARE_EVERY
+#define PHOS_SHARE_EVERY 1      // a round of sharing is tried every n-th iteration of the drain loop
+#endif
+#ifndef PHOS_SHARE_MIN_UNITS
+#define PHOS_SHARE_MIN_UNITS 2
+#endif
 #ifndef PHOS_SHARE_BOTTOM
 #define PHOS_SHARE_BOTTOM 0     // give the bottom stack entry (the largest pending subtrees) instead of the top one
 #endif
@@ -395,6 +404,21 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   }
 
 #if PHOS_TAIL_SHARE
+  uint32_t share_tick = 0;
+  // Coherent streams (camera rays) end warp-wide together: there is little to share and the exchange only costs (-2.5 %
+  // on config 2, profiles/r02_summary.md).  A warp whose remaining rays all point into ONE octant takes that as the sign
+  // of a coherent stream and does not share; bounce and shadow streams mix octants in every warp.
+  // (This exact form — an int threshold, the tick — is the measured one: a stateless test inside the sharing round and a
+  // bool flag both compiled to a slower hot loop, profiles/r02_sweep_share_coherence.log.)
+  int share_min_idle = PHOS_SHARE_MIN_IDLE;
+#if PHOS_SHARE_COHERENCE_TEST
+  {
+    const unsigned with_ray = __ballot_sync(0xffffffffu, has_ray);
+    int same = 0;
+    if (has_ray) __match_all_sync(with_ray, rd.oct, &same);
+    if (__any_sync(0xffffffffu, has_ray && same)) share_min_idle = 33;
+  }
+#endif
   // ---- phase 2: nothing left to refill from — lanes without work help the lanes that still have a ray ---------------
   // A helper holds a copy of the ray (flag bit 31, `ridx` = the lane that owns the ray) and one group of pending siblings
   // taken off the owner's stack (the same ray, a disjoint part of the tree); when it runs out of work its hit is merged
@@ -410,7 +434,13 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
     ++pr_iters;
     pr_lanes += __popc(tl | nl);
 #endif
-    if ((tl | nl) != 0xffffffffu) {
+    // the block below runs when a lane has finished (hand over / retire) or when enough lanes are free for a round of sharing
+    // (the rest of the drain pays two ballots, not the whole protocol)
+    const unsigned fin_any = __ballot_sync(0xffffffffu, has_ray && !tri_work && !node_work);
+    const unsigned free_now = __ballot_sync(0xffffffffu, !has_ray);
+    if (free_now == 0xffffffffu) break;  // every lane retired
+    ++share_tick;
+    if (fin_any != 0u || (__popc(free_now) >= share_min_idle && (share_tick % PHOS_SHARE_EVERY) == 0u)) {
       // helpers that are done hand their record to the owner
       unsigned fh = __ballot_sync(0xffffffffu, has_ray && !tri_work && !node_work && (r.flags & kHelper));
       bool changed = fh != 0u;
@@ -444,11 +474,14 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
       // free lanes take a group of pending siblings each from the lanes that can spare one: the top entry of the stack,
       // or, with an empty stack, all but the nearest pending child of the current group
       const unsigned pend = cur.y >> 8;
-      const bool can_give = busy && ((sp > 0 && (sp > 1 || pend != 0u || lt != 0u)) ||
-                                     (PHOS_SHARE_SPLIT_CUR && (pend & (pend - 1u)) != 0u));  // and keep some
+      // (a lane gives only when it holds at least PHOS_SHARE_MIN_UNITS stacked groups + pending children: rays about to end
+      // are not worth the exchange — coherent streams end warp-wide together and lost 2.5 % to it)
+      const bool can_give = busy && sp + __popc(pend) >= PHOS_SHARE_MIN_UNITS &&
+                            ((sp > 0 && (sp > 1 || pend != 0u || lt != 0u)) ||
+                             (PHOS_SHARE_SPLIT_CUR && (pend & (pend - 1u)) != 0u));  // and keep some
       const unsigned idle = __ballot_sync(0xffffffffu, !has_ray), don = __ballot_sync(0xffffffffu, can_give);
       if (idle == 0xffffffffu) break;  // every lane retired
-      if (__popc(idle) >= PHOS_SHARE_MIN_IDLE && don != 0u) {
+      if (__popc(idle) >= share_min_idle && don != 0u) {
         const int pairs = min(__popc(idle), __popc(don));
         const bool take = !has_ray && __popc(idle & lt_mask) < pairs;
         const bool give = can_give && __popc(don & lt_mask) < pairs;

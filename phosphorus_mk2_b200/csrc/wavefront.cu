@@ -51,7 +51,7 @@ struct FrameArgs {
   float* rad_final;  // per path, [3][Q]: what film_accumulate sums, in sample order
   uint32_t bounce;
   float* n;
-  float* light_pdf;
+  float* lightw;  // per slot, [4][Q]: (light.e * 4) and 1 / pdf of the next-event sample (shade_nee -> integrate)
   uint32_t* count;  // [2]
 };
 
@@ -135,7 +135,7 @@ __device__ __forceinline__ void shade_nee_slot(const FrameArgs& A, const phos_ra
   const v3 a = scene_vert(A.scene, lm & 0xffffu, lf, 0), b = scene_vert(A.scene, lm & 0xffffu, lf, 1),
            c = scene_vert(A.scene, lm & 0xffffu, lf, 2);
   const v3 L = add(add(scl(a, bu), scl(b, bv)), scl(c, 1 - bu - bv));  // barycentric_to_point (mesh.cpp:314-316)
-  A.light_pdf[i] = (1.0f / A.scene.light_area[l]) / nl;
+  const float light_pdf = (1.0f / A.scene.light_area[l]) / nl;
   const v3 so = add(P, scl(n, 0.0001f));  // simd::offset
   v3 wi = sub(L, so);
   const float l2 = __fmaf_rn(wi.x, wi.x, __fmaf_rn(wi.y, wi.y, __fmul_rn(wi.z, wi.z)));
@@ -155,6 +155,20 @@ __device__ __forceinline__ void shade_nee_slot(const FrameArgs& A, const phos_ra
   sh.u[i] = bu;
   sh.v[i] = bv;
   sh.flags[i] = ish ? PHOS_SHADOW : (PHOS_SHADOW | PHOS_MASKED);
+  // The light's side of li() (spt.hpp:237-249) is known here: (light.e * 4) and 1 / pdf with pdf = light pdf * d^2 /
+  // |n_light . -wi|.  `integrate` multiplies by the BSDF value if the shadow ray arrives — it reads these 4 floats instead
+  // of the light's ids off the shadow ray, its vertices, normal and material (a shadow ray that is not hit keeps d = dist).
+  if (ish) {
+    const v3 light_n = shading_normal(A.scene, lm & 0xffffu, lf, bu, bv);
+    const DevMaterial* lmt = A.scene.mats + (lm >> 16);
+    const float pdf = light_pdf * dist * dist / fabsf(dot(light_n, neg(wi)));
+    const v3 le4 = scl(V(__ldg(&lmt->e[0]), __ldg(&lmt->e[1]), __ldg(&lmt->e[2])), 4);
+    const size_t Q = A.Q;
+    A.lightw[i] = le4.x;
+    A.lightw[i + Q] = le4.y;
+    A.lightw[i + 2 * Q] = le4.z;
+    A.lightw[i + 3 * Q] = 1.0f / pdf;
+  }
 }
 
 // Grid-stride over the live slots (the queue length lives in HBM) on a grid capped at kGridStrideBlocksPerSm blocks
@@ -318,12 +332,7 @@ __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kern
     if (!(sflags & (PHOS_HIT | PHOS_MASKED)) && nlobes != 0) {  // li(), spt.hpp:212-255; a 0-lobe BSDF evaluates to 0
       const v3 swi = V(sh.wx[i], sh.wy[i], sh.wz[i]);
       const v3 f = bsdf_f(mt, n, swi, wo);
-      const uint32_t lm = sh.mesh[i];
-      const v3 light_n = shading_normal(A.scene, lm & 0xffffu, sh.face[i], sh.u[i], sh.v[i]);
-      const DevMaterial* lmt = A.scene.mats + (lm >> 16);
-      const float sd = sh.d[i];
-      const float pdf = A.light_pdf[i] * sd * sd / fabsf(dot(light_n, neg(swi)));
-      const v3 li = scl(mul(scl(V(__ldg(&lmt->e[0]), __ldg(&lmt->e[1]), __ldg(&lmt->e[2])), 4), f), 1.0f / pdf);  // (light.e * 4) * f * (1 / pdf)
+      const v3 li = scl(mul(V(A.lightw[i], A.lightw[i + Q], A.lightw[i + 2 * Q]), f), A.lightw[i + 3 * Q]);  // (light.e * 4) * f * (1 / pdf)
       rad = add(rad, mul(beta, li));
     }
     ++depth;
@@ -482,7 +491,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   // 4 Mi paths the tails were a quarter of a config-4 frame (profiles/r01_render_wavefront_size.log: 4 / 8 / 16 / 32 /
   // 64 Mi paths = 513 / 582 / 628 / 656 / 670 M samples/s).  64 Mi paths (over both wavefronts) are 13 GB of wavefront
   // state (kBytesPerPath per path) on a 180 GB device; never more than a quarter of what is free.  PHOS_WAVEFRONT_PATHS overrides.
-  constexpr uint64_t kBytesPerPath = 236ull;  // ensure_wavefront: 3 ray streams, slot maps, normals, pdf, 2 x (beta, rad), rad_final, perm
+  constexpr uint64_t kBytesPerPath = 248ull;  // ensure_wavefront: 3 ray streams, slot maps, normals, light terms, 2 x (beta, rad), rad_final, perm
   uint64_t target = 64ull << 20;
   if (R.paths_cap == 0) {  // asked once per scene upload: cudaMemGetInfo is a driver round trip, not something for every frame
     size_t free_b = 0, total_b = 0;
@@ -553,7 +562,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
     A.rad_final = W.rad_final;
     A.bounce = 0;
     A.n = W.n;
-    A.light_pdf = W.light_pdf;
+    A.lightw = W.lightw;
     A.count = W.count;
   }
   // the second stream starts after the set-up on the first (pixel tables, jitter table); film_accumulate launches are
@@ -692,7 +701,7 @@ int phos_cuda_wavefront_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_t
   A.rad_final = W.rad_final;
   A.bounce = 0;
   A.n = W.n;
-  A.light_pdf = W.light_pdf;
+  A.lightw = W.lightw;
   A.count = W.count;
   const uint32_t blocks = (P + 255) / 256;
   const uint32_t gs_blocks = std::min<uint32_t>(blocks, (uint32_t)ctx->sm_count * kGridStrideBlocksPerSm);
