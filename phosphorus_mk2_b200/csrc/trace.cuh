@@ -27,7 +27,10 @@
 // a per-group distance bound (costed on the host emulation, not built); round 2 (profiles/r02_summary.md): guided
 // (shrinking) claims near the end of the stream (-3..5 %: small chunks starve the refill), handing the second triangle of a
 // pair to a lane with nothing to test through shared memory (one Moeller-Trumbore sequence per step instead of two:
-// -3.5 % coherent, -4.6 % bounce rays — the exchange costs more issue slots than the second test).
+// -3.5 % coherent, -4.6 % bounce rays — the exchange costs more issue slots than the second test); prefetch.global.L1 of
+// the first triangle of the nearest hit leaf / of the next node at the end of a node step (the two fetches are 22 % of the
+// stall samples, profiles/r02_trace_config3_bounce_raw.csv): -5..7 %, every extra instruction costs more than the latency
+// it hides; 8 CTAs per SM at 64 registers: -2..3 %.
 #pragma once
 #include "trace_ray.cuh"
 
