@@ -625,8 +625,15 @@ def dropin_frame_leg(run: Run, scene, spp: int, depth: int):
                    f"add_tile per tile); {wall - secs:.1f} s of scene set-up + the reference's BVH build + upload excluded"}
 
 
-def config1(run: Run):
+def checker(run: Run):
+    """The oracle — only in the CPU legs (parity check / cpu_baseline) of rank 0 at N = 1."""
+    if not run.cpu_legs:
+        return None
     from oracle.pyoracle import Oracle
+    return Oracle()
+
+
+def config1(run: Run):
     from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
     scene = scenes.cornell_box()
     dev = CudaDevice.make(Options(64, 1, 8), run.local)
@@ -638,7 +645,7 @@ def config1(run: Run):
         rs = run.reflib().scene(scene)
         rs.build()
     rec = {"workload": LABELS["cornell"]}
-    rec["streams"] = frame_streams(run, dev, acc, scene, "cornell", ("primary", "shadow"), steps=8, rs=rs, orc=Oracle() if run.cpu_legs else None)
+    rec["streams"] = frame_streams(run, dev, acc, scene, "cornell", ("primary", "shadow"), steps=8, rs=rs, orc=checker(run))
     rec["frame"] = render_frames(run, dev, scene, 64, 8, "tiles", steps=8, warmup=2)
     if run.cpu_legs:
         rec["frame"]["cpu_baseline"] = reference_frame_leg(run, scene, 16, 8)
@@ -647,7 +654,6 @@ def config1(run: Run):
 
 
 def config3(run: Run):
-    from oracle.pyoracle import Oracle
     from phosphorus_mk2_b200.device import Accel, CudaDevice, Options
     scene = scenes.terrain()
     dev = CudaDevice.make(Options(), run.local)
@@ -661,7 +667,7 @@ def config3(run: Run):
         rs = run.reflib().scene(scene)
         rs.build()  # the reference's own single-threaded builder: ~20 s at 10 M triangles, excluded from every figure
     st = dev.accel_stats()
-    rec = frame_streams(run, dev, acc, scene, "terrain", ("bounce", "shadow"), steps=8, rs=rs, orc=Oracle() if run.cpu_legs else None)
+    rec = frame_streams(run, dev, acc, scene, "terrain", ("bounce", "shadow"), steps=8, rs=rs, orc=checker(run))
     for r in rec.values():
         r["workload"] = LABELS["terrain"]
         r["triangles"] = scene.num_triangles()

@@ -470,11 +470,17 @@ struct phos_bvh {
   double seconds = 0.0;
 };
 
+namespace phos {
+bool scene_indices_ok(const phos_scene_desc* d);  // phos_cuda.cu
+}
+
 extern "C" {
 
 phos_bvh* phos_bvh_build(const phos_scene_desc* scene, int threads) {
   using namespace phos;
-  if (!scene) return nullptr;
+  if (!scene || !scene->num_meshes || !scene->vert_offset || !scene->vertices || !scene->face_offset || !scene->faces ||
+      !scene_indices_ok(scene))  // a face with a vertex index outside its mesh would be read out of bounds right below
+    return nullptr;
   const int nthreads = threads > 0 ? std::min(threads, 64) : worker_count();
   uint32_t grain = 1u << 15;  // ranges below this are one task (PHOS_BUILD_GRAIN: tests use a tiny one)
   if (const char* e = std::getenv("PHOS_BUILD_GRAIN")) grain = (uint32_t)std::max(8, std::atoi(e));

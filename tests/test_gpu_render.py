@@ -373,3 +373,54 @@ def test_reduced_config5_scene_matches_oracle(oracle):
     got, _ = render_gpu(sc, acc, 8, 6, 17, ranges=[(0, 4), (4, 8)])
     assert np.isfinite(got).all() and want[..., :3].mean() > 1e-3
     assert mean_rel_err(got, want) < 1e-3
+
+
+def test_malformed_scene_is_refused_on_the_host():
+    """A face whose vertex index lies outside its mesh must fail with PHOS_ERR_INVALID in upload_scene / build_accel: on the
+    device it would be an out-of-bounds read, and a device fault is sticky (it kills the context)."""
+    sc = scenes.cornell_box(32, 32)
+    sc.meshes[1].faces[3, 1] = 10_000
+    dev = CudaDevice.make(Options(1, 1, 2), 0)
+    with pytest.raises(PhosError, match="vertex index"):
+        dev.upload_scene(sc)
+    with pytest.raises(PhosError, match="vertex index"):
+        dev.build_accel(sc)
+    ok = scenes.cornell_box(32, 32)  # the context is still usable
+    acc = Accel(ok)
+    dev.preprocess(ok, acc)
+    dev.upload_scene(ok)
+    dev.render(make_tiles(32, 32), 0, 1, 1, 3)
+    assert np.isfinite(dev.film_read()).all()
+    dev.close()
+
+
+def test_path_depth_zero_still_traces_the_primary_rays(oracle):
+    """path_depth 0: the reference's loop tests the depth AFTER the first bounce (spt.hpp:307-328), so the frame shows what the
+    primary rays see — emitters and the environment — not black."""
+    sc = scenes.cornell_lobes(48, 48)
+    acc = Accel(sc)
+    want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), 4, 1, 0, seed=2)
+    got, _ = render_gpu(sc, acc, 4, 0, 2)
+    assert want[..., :3].max() > 0.1
+    assert mean_rel_err(got, want) < 1e-3
+
+
+def test_more_ranks_than_samples():
+    """samples_of_rank hands some ranks an empty range when spp < world: render_partition renders nothing there and the sum of
+    the films is still the frame."""
+    from phosphorus_mk2_b200.frame import render_partition, samples_of_rank
+    sc = scenes.cornell_box(64, 64)
+    acc = Accel(sc)
+    whole, _ = render_gpu(sc, acc, 2, 4, 8)
+    tiles = make_tiles(64, 64)
+    total = np.zeros_like(whole)
+    ranges = [samples_of_rank(2, r, 5) for r in range(5)]
+    assert any(a == b for a, b in ranges)
+    dev = CudaDevice.make(Options(2, 1, 4), 0)
+    dev.preprocess(sc, acc)
+    dev.upload_scene(sc)
+    for rng in ranges:
+        render_partition(dev, tiles, rng, 2, seed=8)
+        total += dev.film_read()
+    dev.close()
+    assert np.allclose(total[..., :3], whole[..., :3], rtol=2e-6, atol=1e-7)

@@ -74,3 +74,13 @@ def test_fewer_than_eight_triangles_builds_no_node():
                [(m, np.arange(2))]))
     a = Accel(s)
     assert a.num_nodes == 0 and a.num_packets == 0
+
+
+def test_host_build_refuses_a_face_outside_its_mesh():
+    """phos_bvh_build validates vertex indices before it reads vertices through them."""
+    import pytest
+    from phosphorus_mk2_b200.lib import PhosError
+    sc = scenes.cornell_box(32, 32)
+    sc.meshes[0].faces[0, 2] = 4_000_000
+    with pytest.raises(PhosError):
+        Accel(sc)
