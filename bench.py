@@ -438,6 +438,11 @@ def headline(run: Run, scene, label):
     e2e_s = run.max_over_ranks(e2e_s)
     e2e = world * n * e2e_steps / e2e_s / 1e6
     e2e_ok = bool(np.array_equal(hrays.flags, result.flags) and np.array_equal(hrays.d.view(np.uint32), result.d.view(np.uint32)))
+    # what came down: d + flags (8 B) for every ray of a group of four with at least one hit (groups of closest-hit rays none of
+    # which was hit are not written back), the surface record (16 B) per hit
+    groups = result.hit[: n // 4 * 4].reshape(-1, 4).any(axis=1)
+    skip = os.environ.get("PHOS_E2E_SKIP_UNCHANGED", "1") != "0"
+    d2h_bytes = int((32 * int(groups.sum()) + 8 * (n % 4) if skip else 8 * n) + 16 * hits)
     hrays.free()
 
     # ---- CPU baseline + oracle counts (rank 0, N = 1 only) ------------------------------------------
@@ -471,7 +476,7 @@ def headline(run: Run, scene, label):
             "details": {"packed_nodes": st.nodes, "packed_bytes": int(st.bytes_nodes + st.bytes_triangles),
                         "hit_fraction": hits / n, "preprocess_s": prep_s, "wall_s_timed_loop": wall},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 8 * n + 16 * hits,
+            "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "matches_device_path": e2e_ok, "host_cpus_bound": numa_cpus},
             "any_hit": any_hit,
             "roofline": roof, "cpu_baseline": cpu, "parity": parity}
