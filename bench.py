@@ -438,11 +438,7 @@ def headline(run: Run, scene, label):
     e2e_s = run.max_over_ranks(e2e_s)
     e2e = world * n * e2e_steps / e2e_s / 1e6
     e2e_ok = bool(np.array_equal(hrays.flags, result.flags) and np.array_equal(hrays.d.view(np.uint32), result.d.view(np.uint32)))
-    # what came down: d + flags (8 B) for every ray of a group of four with at least one hit (groups of closest-hit rays none of
-    # which was hit are not written back), the surface record (16 B) per hit
-    groups = result.hit[: n // 4 * 4].reshape(-1, 4).any(axis=1)
-    skip = os.environ.get("PHOS_E2E_SKIP_UNCHANGED", "1") != "0"
-    d2h_bytes = int((32 * int(groups.sum()) + 8 * (n % 4) if skip else 8 * n) + 16 * hits)
+    d2h_bytes = 8 * n + 16 * hits  # d + flags for every ray, the surface record where the traversal wrote one
     hrays.free()
 
     # ---- CPU baseline + oracle counts (rank 0, N = 1 only) ------------------------------------------

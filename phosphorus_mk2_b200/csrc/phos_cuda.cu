@@ -79,18 +79,12 @@ bool alloc_rays(phos_ctx* ctx, uint64_t n, phos_rays& out) {
 // reference src/triangle.hpp:28-31).  That is what lets the up-link carry 32 B per ray instead of 48: the
 // surface record of rays that miss, and of shadow rays (it holds the sampled light's ids, spt.hpp:120-124),
 // never has to visit the device to come back untouched.  Four rays per thread, 16-byte stores, grid-stride.
-__global__ void __launch_bounds__(256) writeback_kernel(const phos_rays dev, const phos_rays host, uint32_t n, int skip_unchanged) {
+__global__ void __launch_bounds__(256) writeback_kernel(const phos_rays dev, const phos_rays host, uint32_t n) {
  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; i < n; i += gridDim.x * blockDim.x * 4u) {
   if (i + 4u <= n) {
     const uint4 m = *reinterpret_cast<const uint4*>(dev.mesh + i);
-    const uint4 f = *reinterpret_cast<const uint4*>(dev.flags + i);
-    // A closest-hit ray that was not hit keeps its d and flags: four such rays in a row (coherent streams miss in runs) are
-    // not written back at all.  An accepted SHADOW ray changes d / flags without touching the surface record, so any SHADOW
-    // ray in the group sends the group's d / flags down.
-    const bool none4 = (m.x & m.y & m.z & m.w) == 0xffffffffu && !((f.x | f.y | f.z | f.w) & PHOS_SHADOW);
-    if (none4 && skip_unchanged) continue;
     *reinterpret_cast<float4*>(host.d + i) = *reinterpret_cast<const float4*>(dev.d + i);
-    *reinterpret_cast<uint4*>(host.flags + i) = f;
+    *reinterpret_cast<uint4*>(host.flags + i) = *reinterpret_cast<const uint4*>(dev.flags + i);
     const bool all4 = m.x != 0xffffffffu && m.y != 0xffffffffu && m.z != 0xffffffffu && m.w != 0xffffffffu;
     if (all4) {
       *reinterpret_cast<uint4*>(host.mesh + i) = m;
@@ -422,8 +416,6 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
   // (profiles/r01_e2e_pipeline.log: 1.98-2.01 -> 1.84-1.88 ms per 2 M-ray frame at 256 Ki-ray chunks)
   int in_streams = 2;
   if (const char* e = std::getenv("PHOS_E2E_IN_STREAMS")) in_streams = std::atoi(e);
-  int skip_unchanged = 1;  // groups of four closest-hit rays none of which was hit are not written back (PHOS_E2E_SKIP_UNCHANGED=0: always)
-  if (const char* e = std::getenv("PHOS_E2E_SKIP_UNCHANGED")) skip_unchanged = std::atoi(e) != 0;
   int wb_ctas = 4;
   if (const char* e = std::getenv("PHOS_E2E_WB_CTAS")) wb_ctas = std::max(1, std::atoi(e));
   const char* dbg = std::getenv("PHOS_E2E_DEBUG");  // timing probes only (tools/e2e_probe.py): "noin" / "noout" skip a stage
@@ -462,7 +454,7 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
       h.face += base;
       h.flags += base;
       const unsigned full = (unsigned)((cnt + 1023) / 1024);
-      writeback_kernel<<<std::min<unsigned>(full, (unsigned)wb_ctas), 256, 0, ctx->s_out>>>(L.rays, h, (uint32_t)cnt, skip_unchanged);
+      writeback_kernel<<<std::min<unsigned>(full, (unsigned)wb_ctas), 256, 0, ctx->s_out>>>(L.rays, h, (uint32_t)cnt);
       ctx->launches++;
       ok = cuda_ok(ctx, cudaGetLastError(), "writeback_kernel launch");
     } else if (ok && pitched && !dbg_noout) {  // rows 6..11 of the slab: d, flags, mesh, face, u, v

@@ -108,34 +108,6 @@ def test_pinned_stream_sparse_write_back(device, oracle, monkeypatch):
         assert np.array_equal(a[closest], b[closest]), f
 
 
-def test_write_back_skips_groups_of_unhit_rays(device, oracle, monkeypatch):
-    """Closest-hit rays that are not hit keep d and flags, so the zero-copy write-back leaves groups of four such rays alone
-    (fewer bytes down the link).  Mostly-missing random rays with recognisable d / flags / surface records: every field as
-    the oracle has it, with the skip on and off."""
-    sc = scenes.heightfield(64)
-    acc = Accel(sc)
-    device.preprocess(sc, acc)
-    nodes, packets = acc.nodes_array(), acc.packets_array()
-    n = 4096 * 3 + 5
-    src = raysets.random_rays(sc, n, seed=91)
-    aimed = raysets.aimed_rays(sc, n, seed=92)
-    for f in ("px", "py", "pz", "wx", "wy", "wz"):
-        getattr(src, f)[::7] = getattr(aimed, f)[::7]  # a hit here and there
-    src.d[:] = np.linspace(50.0, 90.0, n, dtype=np.float32)  # finite, distinct tmax values that must survive on misses
-    src.mesh[:] = 0xABCD0002
-    src.face[:] = 77
-    want, _ = oracle.traverse(nodes, packets, src)
-    assert 0.02 < want.hit.mean() < 0.6
-    for mode in ("1", "0"):
-        monkeypatch.setenv("PHOS_E2E_SKIP_UNCHANGED", mode)
-        pr = pinned_ray_batch(n)
-        for f in ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags"):
-            getattr(pr, f)[:] = getattr(src, f)
-        device.trace(pr)
-        assert len(mismatches(src, pr, want)) == 0, mode
-        assert np.array_equal(bits(pr.d), bits(want.d)) and np.array_equal(pr.flags, want.flags)
-
-
 def test_empty_stream_and_call_order_errors(device):
     fresh = CudaDevice.make(Options(), 0)
     with pytest.raises(PhosError):
