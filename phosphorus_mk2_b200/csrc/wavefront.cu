@@ -50,6 +50,7 @@ struct FrameArgs {
   float* rad_out;
   float* rad_final;  // per path, [3][Q]: what film_accumulate sums, in sample order
   uint32_t bounce;
+  uint32_t export_light_ids;  // shade_nee also writes mesh / face / u / v of the shadow rays (16 B per slot nobody reads in a frame)
   float* n;
   float* lightw;  // per slot, [4][Q]: (light.e * 4) and 1 / pdf of the next-event sample (shade_nee -> integrate)
   uint32_t* count;  // [2]
@@ -150,10 +151,12 @@ __device__ __forceinline__ void shade_nee_slot(const FrameArgs& A, const phos_ra
   sh.wy[i] = wi.y;
   sh.wz[i] = wi.z;
   sh.d[i] = dist;
-  sh.mesh[i] = lm;  // the sampled light's ids ride on the shadow ray (spt.hpp:120-124)
-  sh.face[i] = lf;
-  sh.u[i] = bu;
-  sh.v[i] = bv;
+  if (A.export_light_ids) {  // the sampled light's ids ride on the shadow ray (spt.hpp:120-124): only the exported stream needs
+    sh.mesh[i] = lm;         // them (phos_cuda_wavefront_rays) — inside a frame `integrate` gets the light's side of li() below
+    sh.face[i] = lf;
+    sh.u[i] = bu;
+    sh.v[i] = bv;
+  }
   sh.flags[i] = ish ? PHOS_SHADOW : (PHOS_SHADOW | PHOS_MASKED);
   // The light's side of li() (spt.hpp:237-249) is known here: (light.e * 4) and 1 / pdf with pdf = light pdf * d^2 /
   // |n_light . -wi|.  `integrate` multiplies by the BSDF value if the shadow ray arrives — it reads these 4 floats instead
@@ -561,6 +564,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
     A.rad_in = A.rad_out = W.rad[0];
     A.rad_final = W.rad_final;
     A.bounce = 0;
+    A.export_light_ids = std::getenv("PHOS_SHADE_EXPORT_IDS") ? 1u : 0u;  // (A/B switch of profiles/r02_render_shadow_ids.log)
     A.n = W.n;
     A.lightw = W.lightw;
     A.count = W.count;
@@ -700,6 +704,7 @@ int phos_cuda_wavefront_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_t
   A.rad_in = A.rad_out = W.rad[0];
   A.rad_final = W.rad_final;
   A.bounce = 0;
+  A.export_light_ids = 1;
   A.n = W.n;
   A.lightw = W.lightw;
   A.count = W.count;
