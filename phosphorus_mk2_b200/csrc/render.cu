@@ -333,10 +333,9 @@ static void release_one(Wavefront& wf) {
 }
 
 bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixels, int which) {
-  Wavefront& wf = which ? this->wf2 : this->wf;
+  Wavefront& wf = wfs[which];
   if (wf.capacity < paths || wf.pixel_capacity < pixels) {
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->s_cmp);
+    for (cudaStream_t s : {ctx->stream, ctx->s_cmp, ctx->s_in, ctx->s_out}) cudaStreamSynchronize(s);  // the wavefront streams
     release_one(wf);
     const uint64_t cap = std::max<uint64_t>(paths, 1024);
     bool ok = alloc_rays(ctx, cap, wf.rays[0]) && alloc_rays(ctx, cap, wf.rays[1]) && alloc_rays(ctx, cap, wf.shadow);
@@ -364,8 +363,7 @@ bool RenderState::ensure_wavefront(phos_ctx* ctx, uint64_t paths, uint64_t pixel
 }
 
 void RenderState::release_wavefront() {
-  release_one(wf);
-  release_one(wf2);
+  for (Wavefront& w : wfs) release_one(w);
 }
 
 bool RenderState::set_tiles(phos_ctx* ctx, const phos_tile* tiles, const unsigned long long* offsets, uint32_t n) {

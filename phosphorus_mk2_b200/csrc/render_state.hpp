@@ -48,8 +48,10 @@ struct RenderState {
   float* d_jitter = nullptr;
   uint32_t jitter_capacity = 0;
   uint64_t paths_cap = 0;  // most paths in flight the device memory affords (asked once per scene upload; 0 = not yet)
-  Wavefront wf;   // the wavefront of a frame (and of phos_cuda_wavefront_rays)
-  Wavefront wf2;  // second wavefront: batches of a frame alternate between two streams (wavefront.cu)
+  // the wavefronts of a frame: its sample batches go round-robin over up to kMaxWavefronts wavefronts on as many streams
+  // (wavefront.cu); wfs[0] also serves phos_cuda_wavefront_rays
+  static constexpr int kMaxWavefronts = 4;
+  Wavefront wfs[kMaxWavefronts];
 
   int upload(phos_ctx* ctx, const phos_scene_desc* scene);
   bool set_tiles(phos_ctx* ctx, const phos_tile* tiles, const unsigned long long* offsets, uint32_t n);

@@ -498,32 +498,37 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   uint64_t target = 64ull << 20;
   if (R.paths_cap == 0) {  // asked once per scene upload: cudaMemGetInfo is a driver round trip, not something for every frame
     size_t free_b = 0, total_b = 0;
+    uint64_t held = 0;
+    for (const Wavefront& w : R.wfs) held += w.capacity;
     R.paths_cap = ~0ull;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-      R.paths_cap = std::max<uint64_t>(((uint64_t)free_b + (R.wf.capacity + R.wf2.capacity) * kBytesPerPath) / 4ull / kBytesPerPath, 1ull << 20);
+      R.paths_cap = std::max<uint64_t>(((uint64_t)free_b + held * kBytesPerPath) / 4ull / kBytesPerPath, 1ull << 20);
     else
       cudaGetLastError();
   }
   target = std::min<uint64_t>(target, R.paths_cap);
   if (const char* e = std::getenv("PHOS_WAVEFRONT_PATHS")) target = std::max<uint64_t>(1ull << 16, std::strtoull(e, nullptr, 10));
-  // Two wavefronts (PHOS_WAVEFRONTS=2, off by default): the batches of a frame alternate between two streams, so the
-  // tail of one batch's launches (a launch cannot end before its longest ray does) runs under the other batch's full
-  // launches.  Film accumulation stays in sample order (an event chains the two streams there), so the image does not
-  // depend on it.  Measured on one GPU (profiles/r01_render_wavefront_size.log): config 4 215.6 -> 211.9 ms per frame,
-  // but the Cornell box 15.8 -> 19.7 ms (short rays, no tails to hide; the two wavefronts only contend) — hence off;
-  // the case it is meant for is the tile-partitioned frame on 8 GPUs, where each rank is left with a single batch.
+  // Several wavefronts: the sample batches of a frame go round-robin over nw wavefronts on nw streams.  r01 had this off
+  // (the tail of one batch's launches under the other's full launches bought 1.7 % on config 4 and cost 20 % on the Cornell
+  // box); with the round-2 shading kernels, which are bound by memory latency while the traversal is bound by issue slots,
+  // the two overlap: config 4 747 -> 764 M samples/s, Cornell box 1296 -> 1383, 30 M-triangle field 576 -> 585
+  // (profiles/r02_render_wavefronts.log) — two wavefronts by default (PHOS_WAVEFRONTS=1..4).  Film accumulation stays in
+  // sample order (events chain the streams there), so the image does not depend on it.
   // Always one wavefront when the NORMALS channel is on (its "last sample that hit" is order dependent).
-  int nw = 1;
-  if (const char* e = std::getenv("PHOS_WAVEFRONTS")) nw = std::atoi(e) >= 2 ? 2 : 1;
-  if (R.film_normals || spp_end - spp_begin < 2) nw = 1;
+  int nw = 2;
+  if (const char* e = std::getenv("PHOS_WAVEFRONTS")) nw = std::max(1, std::min(RenderState::kMaxWavefronts, std::atoi(e)));
+  if (R.film_normals) nw = 1;
+  nw = (int)std::min<uint32_t>((uint32_t)nw, spp_end - spp_begin);
   uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(spp_end - spp_begin, target / ((uint64_t)P * nw)));
-  if (nw == 2) batch = std::min<uint32_t>(batch, (spp_end - spp_begin + 1) / 2);  // at least two batches to overlap
+  if (nw > 1) batch = std::min<uint32_t>(batch, (spp_end - spp_begin + nw - 1) / nw);  // at least nw batches to overlap
   for (int w = 0; w < nw; ++w)
     if (!R.ensure_wavefront(ctx, (uint64_t)P * batch, P, w)) return PHOS_ERR_CUDA;
   if (!R.set_tiles(ctx, tiles, offsets.data(), n_tiles)) return PHOS_ERR_CUDA;
-  Wavefront* WF[2] = {&R.wf, &R.wf2};
+  Wavefront* WF[RenderState::kMaxWavefronts];
+  for (int w = 0; w < RenderState::kMaxWavefronts; ++w) WF[w] = &R.wfs[w];
   cudaStream_t st = ctx->stream;
-  cudaStream_t streams[2] = {ctx->stream, ctx->s_cmp};
+  // (the extra streams are those of the host-pointer query pipeline: one host thread drives a context, never both at once)
+  cudaStream_t streams[RenderState::kMaxWavefronts] = {ctx->stream, ctx->s_cmp, ctx->s_in, ctx->s_out};
 
   for (int w = 0; w < nw; ++w)
   for (uint32_t first = 0; first < n_tiles; first += 65535) {
@@ -548,7 +553,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
     cudaStreamSynchronize(st);  // jit goes out of scope
   }
 
-  FrameArgs AW[2];
+  FrameArgs AW[RenderState::kMaxWavefronts];
   for (int w = 0; w < nw; ++w) {
     FrameArgs& A = AW[w];
     const Wavefront& W = *WF[w];
@@ -571,14 +576,12 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   }
   // the second stream starts after the set-up on the first (pixel tables, jitter table); film_accumulate launches are
   // chained in batch order; the first stream ends by waiting for the second
-  cudaEvent_t ev_setup = nullptr, ev_film[2] = {nullptr, nullptr};
+  cudaEvent_t ev_setup = nullptr, ev_film[RenderState::kMaxWavefronts] = {nullptr, nullptr, nullptr, nullptr};
   bool ok = true;
-  if (nw == 2) {
-    ok = cuda_ok(ctx, cudaEventCreateWithFlags(&ev_setup, cudaEventDisableTiming), "event") &&
-         cuda_ok(ctx, cudaEventCreateWithFlags(&ev_film[0], cudaEventDisableTiming), "event") &&
-         cuda_ok(ctx, cudaEventCreateWithFlags(&ev_film[1], cudaEventDisableTiming), "event") &&
-         cuda_ok(ctx, cudaEventRecord(ev_setup, st), "event record") &&
-         cuda_ok(ctx, cudaStreamWaitEvent(streams[1], ev_setup, 0), "event wait");
+  if (nw > 1) {
+    ok = cuda_ok(ctx, cudaEventCreateWithFlags(&ev_setup, cudaEventDisableTiming), "event") && cuda_ok(ctx, cudaEventRecord(ev_setup, st), "event record");
+    for (int w = 0; ok && w < nw; ++w) ok = cuda_ok(ctx, cudaEventCreateWithFlags(&ev_film[w], cudaEventDisableTiming), "event");
+    for (int w = 1; ok && w < nw; ++w) ok = cuda_ok(ctx, cudaStreamWaitEvent(streams[w], ev_setup, 0), "event wait");
   }
   // shading classes (above): on unless the scene has a single material or PHOS_SHADE_BIN=0
   bool bin = R.num_materials > 1;
@@ -586,7 +589,7 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
   int rc = PHOS_OK;
   uint32_t k = 0;
   for (uint32_t s0 = spp_begin; ok && rc == PHOS_OK && s0 < spp_end; s0 += batch, ++k) {
-    const int w = nw == 2 ? (int)(k & 1u) : 0;
+    const int w = (int)(k % (uint32_t)nw);
     cudaStream_t sk = streams[w];
     FrameArgs& A = AW[w];
     Wavefront& W = *WF[w];
@@ -630,18 +633,20 @@ int phos_cuda_render(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_tiles, ui
       ctx->launches++;
     }
     if (rc) break;
-    if (nw == 2 && k > 0) ok = cuda_ok(ctx, cudaStreamWaitEvent(sk, ev_film[(k - 1) & 1u], 0), "event wait");  // sample order
+    if (nw > 1 && k > 0) ok = cuda_ok(ctx, cudaStreamWaitEvent(sk, ev_film[(k - 1) % (uint32_t)nw], 0), "event wait");  // sample order
     film_accumulate_kernel<<<(P + 255) / 256, 256, 0, sk>>>(A, R.film);
     ctx->launches++;
-    if (nw == 2) ok = ok && cuda_ok(ctx, cudaEventRecord(ev_film[k & 1u], sk), "event record");
+    if (nw > 1) ok = ok && cuda_ok(ctx, cudaEventRecord(ev_film[k % (uint32_t)nw], sk), "event record");
   }
-  if (nw == 2) {
-    // everything the second stream did is ordered before whatever the caller enqueues next on the first
+  if (nw > 1) {
+    // everything the other streams did is ordered before whatever the caller enqueues next on the first: the film
+    // accumulations are chained, so the last batch's event covers all of them
     if (ok && rc == PHOS_OK && k > 0)
-      ok = cuda_ok(ctx, cudaEventRecord(ev_setup, streams[1]), "event record") && cuda_ok(ctx, cudaStreamWaitEvent(st, ev_setup, 0), "event wait");
+      ok = cuda_ok(ctx, cudaStreamWaitEvent(st, ev_film[(k - 1) % (uint32_t)nw], 0), "event wait");
     else
-      cudaStreamSynchronize(streams[1]);
-    for (cudaEvent_t e : {ev_setup, ev_film[0], ev_film[1]})
+      for (int w = 1; w < nw; ++w) cudaStreamSynchronize(streams[w]);
+    if (ev_setup) cudaEventDestroy(ev_setup);
+    for (cudaEvent_t e : ev_film)
       if (e) cudaEventDestroy(e);
   }
   if (rc) return rc;
@@ -674,7 +679,7 @@ int phos_cuda_wavefront_rays(phos_ctx* ctx, const phos_tile* tiles, uint32_t n_t
   const uint32_t P = (uint32_t)total;
   if (capacity < P) return fail(ctx, PHOS_ERR_INVALID, "output stream too small");
   if (!R.ensure_wavefront(ctx, P, P) || !R.set_tiles(ctx, tiles, offsets.data(), n_tiles)) return PHOS_ERR_CUDA;
-  Wavefront& W = R.wf;
+  Wavefront& W = R.wfs[0];
   cudaStream_t st = ctx->stream;
   pixel_table_kernel<<<dim3((max_px + 255) / 256, n_tiles), 256, 0, st>>>(R.d_tiles, R.d_tile_offsets, R.camera.width, W.pixel);
   std::vector<float> jit;

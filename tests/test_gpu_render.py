@@ -182,8 +182,8 @@ def test_tile_and_sample_partitioning_do_not_change_the_image():
 
 
 def test_batching_and_second_wavefront_do_not_change_the_image(monkeypatch):
-    """The frame is cut into batches of PHOS_WAVEFRONT_PATHS paths, optionally alternating between two wavefronts on two
-    streams (PHOS_WAVEFRONTS=2, film accumulation chained in sample order): same film, bit for bit."""
+    """The frame is cut into batches of PHOS_WAVEFRONT_PATHS paths that go round-robin over 1..4 wavefronts on as many
+    streams (PHOS_WAVEFRONTS, default 2; film accumulation chained in sample order): same film, bit for bit."""
     sc = scenes.cornell_box(96, 64)
     acc = Accel(sc)
     monkeypatch.setenv("PHOS_WAVEFRONTS", "1")
@@ -197,6 +197,16 @@ def test_batching_and_second_wavefront_do_not_change_the_image(monkeypatch):
     monkeypatch.delenv("PHOS_WAVEFRONT_PATHS")
     two_big, _ = render_gpu(sc, acc, 16, 5, 3)  # one batch per wavefront
     assert np.array_equal(whole, two_big)
+    for nw in ("3", "4"):
+        monkeypatch.setenv("PHOS_WAVEFRONTS", nw)
+        monkeypatch.setenv("PHOS_WAVEFRONT_PATHS", "65536")
+        many, _ = render_gpu(sc, acc, 16, 5, 3)
+        assert np.array_equal(whole, many), nw
+        monkeypatch.delenv("PHOS_WAVEFRONT_PATHS")
+        assert np.array_equal(whole, render_gpu(sc, acc, 16, 5, 3)[0]), nw
+    monkeypatch.delenv("PHOS_WAVEFRONTS")
+    assert np.array_equal(whole, render_gpu(sc, acc, 16, 5, 3)[0])  # the default
+    assert np.array_equal(render_gpu(sc, acc, 1, 5, 3)[0], render_gpu(sc, acc, 1, 5, 3)[0])  # fewer samples than wavefronts
 
 
 def test_render_call_order_errors():
