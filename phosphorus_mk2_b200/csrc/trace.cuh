@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   __shared__ uint2 s_stack[kSmemStack * kTraceBlock];
   __shared__ alignas(128) uint32_t s_stage[kTraceWarps][2][8][kChunk];
   __shared__ alignas(8) unsigned long long s_bar[kTraceWarps][2];
+  __shared__ int s_share_min[kTraceWarps];
 
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #ifdef PHOS_TAIL_PROBE
@@ -411,17 +412,23 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   // Coherent streams (camera rays) end warp-wide together: there is little to share and the exchange only costs (-2.5 %
   // on config 2, profiles/r02_summary.md).  A warp whose remaining rays all point into ONE octant takes that as the sign
   // of a coherent stream and does not share; bounce and shadow streams mix octants in every warp.
-  // (This exact form — an int threshold, the tick — is the measured one: a stateless test inside the sharing round and a
-  // bool flag both compiled to a slower hot loop, profiles/r02_sweep_share_coherence.log.)
-  int share_min_idle = PHOS_SHARE_MIN_IDLE;
+  // (The threshold lives in shared memory: held in a register through phase 2 it cost a spill slot in the HOT loop; a
+  // stateless test inside the sharing round and a bool flag compiled to a 4 % slower hot loop,
+  // profiles/r02_sweep_share_coherence.log.)
 #if PHOS_SHARE_COHERENCE_TEST
   {
     const unsigned with_ray = __ballot_sync(0xffffffffu, has_ray);
     int same = 0;
     if (has_ray) __match_all_sync(with_ray, rd.oct, &same);
-    if (__any_sync(0xffffffffu, has_ray && same)) share_min_idle = 33;
+    const bool coherent = __any_sync(0xffffffffu, has_ray && same);
+    if (lane == 0) s_share_min[warp] = coherent ? 33 : PHOS_SHARE_MIN_IDLE;  // kept in shared memory: no register lives through phase 2 for it
+    __syncwarp();
   }
+#else
+  if (lane == 0) s_share_min[warp] = PHOS_SHARE_MIN_IDLE;
+  __syncwarp();
 #endif
+#define share_min_idle (s_share_min[warp])
   // ---- phase 2: nothing left to refill from — lanes without work help the lanes that still have a ray ---------------
   // A helper holds a copy of the ray (flag bit 31, `ridx` = the lane that owns the ray) and one group of pending siblings
   // taken off the owner's stack (the same ray, a disjoint part of the tree); when it runs out of work its hit is merged
@@ -535,6 +542,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
     }
     step(tri_work, node_work, __popc(tl), __popc(nl));
   }
+#undef share_min_idle
 #endif
 #ifdef PHOS_TAIL_PROBE
   if (lane == 0 && P.probe) {
