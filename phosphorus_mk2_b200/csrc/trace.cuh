@@ -30,7 +30,12 @@
 // -3.5 % coherent, -4.6 % bounce rays — the exchange costs more issue slots than the second test); prefetch.global.L1 of
 // the first triangle of the nearest hit leaf / of the next node at the end of a node step (the two fetches are 22 % of the
 // stall samples, profiles/r02_trace_config3_bounce_raw.csv): -5..7 %, every extra instruction costs more than the latency
-// it hides; 8 CTAs per SM at 64 registers: -2..3 %.
+// it hides; 8 CTAs per SM at 64 registers: -2..3 %.  On the eager-commit loop (profiles/r02_sweep_eager_commit.log,
+// r02_sweep_eager_knobs.log): prefetch.global.L1 / .L2 of the next node where its index is committed, a whole loop
+// iteration before the loads: -1..2.5 % (with a second prefetch 64 bytes on: -35 % on the terrain); L1::evict_last on node
+// loads, L1::no_allocate / evict_first on triangle loads: -0..19 %; not staging the next chunk ahead near the end of the
+// stream (claim at half of the current chunk / on demand): loses what the eager commit gained; vote bias 2 / 4, refill at
+// 4 / 8 idle lanes, sharing from 8 / 16 idle lanes: within the noise of the defaults.
 #pragma once
 #include "trace_ray.cuh"
 
@@ -67,9 +72,6 @@ namespace phos {
 #ifndef PHOS_TAIL_SHARE
 #define PHOS_TAIL_SHARE 1
 #endif
-#ifndef PHOS_SHARE_SPLIT_CUR
-#define PHOS_SHARE_SPLIT_CUR 1  // with an empty stack, give away all but the nearest pending child of the current group
-#endif
 #ifndef PHOS_SHARE_MIN_IDLE
 #define PHOS_SHARE_MIN_IDLE 12  // lanes without a ray before a round of sharing starts (1: -3 % on coherent rays, 12: -1.4 %; profiles/r02_tail.md)
 #endif
@@ -82,9 +84,7 @@ namespace phos {
 #ifndef PHOS_SHARE_MIN_UNITS
 #define PHOS_SHARE_MIN_UNITS 2
 #endif
-#ifndef PHOS_SHARE_BOTTOM
-#define PHOS_SHARE_BOTTOM 0     // give the bottom stack entry (the largest pending subtrees) instead of the top one
-#endif
+constexpr uint32_t kNoNode = 0xffffffffu;     // "no node left to test" (Ray traversal state)
 constexpr int kChunk = PHOS_CHUNK;           // rays per claimed chunk
 constexpr int kRefillMin = PHOS_REFILL_MIN;  // idle lanes that trigger a refill
 constexpr int kTraceWarps = kTraceBlock / 32;
@@ -260,7 +260,13 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   rd.oct = 0;
   uint32_t ridx = 0;
   bool has_ray = false;
-  uint2 cur = make_uint2(0u, 0u);
+  // The node this lane tests next.  A node step ENDS by committing the one after it: the nearest pending child of the
+  // node just tested (its siblings go onto the stack as one group), or, when all its children missed, the nearest child
+  // of the group on top of the stack.  So every pending group lives on the stack, a lane carries one node index instead
+  // of a group of siblings, "has node work" is one compare, and a lane without a ray has lt == 0 and node == kNoNode —
+  // the two work predicates of the loop head need no has_ray (+3.5..5 % over popping at the start of the next node step,
+  // profiles/r02_sweep_eager_commit.log).
+  uint32_t node = kNoNode;
   // leaf state: `lt` = hit leaf slots of the current node still to open (key space, bits 0-7) | triangles left
   // in the open leaf (bits 8-11); tptr = next triangle; lcounts / lbase = the node's leaf table
   uint32_t lt = 0, tptr = 0, lcounts = 0, lbase = 0;
@@ -336,22 +342,24 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
           if (kCount) n_tris += adv2 ? 2u : 1u;
           if (done) {  // any-hit: this ray is finished
             lt = 0u;
-            cur.y = 0u;
+            node = kNoNode;
             sp = 0;
           }
         }
       }
     } else if (node_work) {
-      if ((cur.y >> 8) == 0u) cur = pop();
-      if (cur.y >> 8) {
-        const uint32_t node = take_child(cur, rd.oct);
-        if (cur.y >> 8) push(cur);
-        const NodeHits h = node_test(P.accel, node, r.ox, r.oy, r.oz, rd, r.d * PHOS_CULL_SLACK);
-        if (kCount) ++n_nodes;
-        lt = h.leaf;
-        lcounts = h.counts;
-        lbase = h.tri_base;
-        cur = make_uint2(h.child_base, h.imask | (h.inner << 8));
+      const NodeHits h = node_test(P.accel, node, r.ox, r.oy, r.oz, rd, r.d * PHOS_CULL_SLACK);
+      if (kCount) ++n_nodes;
+      lt = h.leaf;
+      lcounts = h.counts;
+      lbase = h.tri_base;
+      uint2 g = make_uint2(h.child_base, h.imask | (h.inner << 8));
+      if ((g.y >> 8) == 0u && sp != 0) g = pop();  // its own children all missed: the nearest group still pending
+      if (g.y >> 8) {
+        node = take_child(g, rd.oct);
+        if (g.y >> 8) push(g);
+      } else {
+        node = kNoNode;
       }
     }
   };
@@ -360,8 +368,8 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   for (;;) {
     if (kCount) ++w_iter;
     // 1. what every lane wants to do next (two ballots drive everything else)
-    const bool tri_work = has_ray && lt != 0u;
-    const bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
+    const bool tri_work = lt != 0u;
+    const bool node_work = !tri_work && node != kNoNode;
     const unsigned tl = __ballot_sync(0xffffffffu, tri_work);
     const unsigned nl = __ballot_sync(0xffffffffu, node_work);
     const int n_tri = __popc(tl), n_node = __popc(nl);  // disjoint sets: the rest of the warp is without work
@@ -390,7 +398,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
               r.u = r.v = 0.0f;
               rd = make_raydir(r.wx, r.wy, r.wz);
               ridx = cur_base + k;
-              cur = make_uint2(0u, 1u | ((1u << rd.oct) << 8));  // the root as a one-node group in slot 0
+              node = 0u;  // the root
               sp = 0;
               lt = 0u;
               has_ray = true;
@@ -436,8 +444,8 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   // owner writes the ray once no helper is left.  The longest ray of a warp no longer runs on one lane while 31 wait.
   for (;;) {
     if (kCount) ++w_iter;
-    bool tri_work = has_ray && lt != 0u;
-    bool node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
+    bool tri_work = lt != 0u;
+    bool node_work = !tri_work && node != kNoNode;
     unsigned tl = __ballot_sync(0xffffffffu, tri_work);
     unsigned nl = __ballot_sync(0xffffffffu, node_work);
 #ifdef PHOS_TAIL_PROBE
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
             r.d = fminf(r.d, hd);
             r.tri = ht;
             lt = 0u;
-            cur.y = 0u;
+            node = kNoNode;
             sp = 0;
           } else {
             accept_hit(P.accel, r, hd, hu, hv, ht);
@@ -475,7 +483,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
         if ((int)lane == h) has_ray = false;
       }
       // owners that are done and have no helper left write their ray
-      const bool busy = has_ray && (lt != 0u || (cur.y >> 8) != 0u || sp != 0);
+      const bool busy = lt != 0u || node != kNoNode;
       const uint32_t group = !has_ray ? 32u + lane : (r.flags & kHelper) ? ridx : lane;
       const unsigned peers = __match_any_sync(0xffffffffu, group);
       const bool leaves = has_ray && !busy && !(r.flags & kHelper) && peers == (1u << lane);
@@ -483,12 +491,9 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
       changed = changed || __any_sync(0xffffffffu, leaves);  // (warp-uniform: it guards warp collectives below)
       // free lanes take a group of pending siblings each from the lanes that can spare one: the top entry of the stack,
       // or, with an empty stack, all but the nearest pending child of the current group
-      const unsigned pend = cur.y >> 8;
-      // (a lane gives only when it holds at least PHOS_SHARE_MIN_UNITS stacked groups + pending children: rays about to end
-      // are not worth the exchange — coherent streams end warp-wide together and lost 2.5 % to it)
-      const bool can_give = busy && sp + __popc(pend) >= PHOS_SHARE_MIN_UNITS &&
-                            ((sp > 0 && (sp > 1 || pend != 0u || lt != 0u)) ||
-                             (PHOS_SHARE_SPLIT_CUR && (pend & (pend - 1u)) != 0u));  // and keep some
+      // every pending group is on the stack, and a lane with a stacked group also holds the node it tests next: it gives
+      // its top entry and keeps that node (profiles/r02_sweep_eager_knobs.log: idle-lane thresholds 8 / 12 / 16 are equal)
+      const bool can_give = sp > 0 && sp + 1 >= PHOS_SHARE_MIN_UNITS;
       const unsigned idle = __ballot_sync(0xffffffffu, !has_ray), don = __ballot_sync(0xffffffffu, can_give);
       if (idle == 0xffffffffu) break;  // every lane retired
       if (__popc(idle) >= share_min_idle && don != 0u) {
@@ -496,21 +501,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
         const bool take = !has_ray && __popc(idle & lt_mask) < pairs;
         const bool give = can_give && __popc(don & lt_mask) < pairs;
         uint2 g = make_uint2(0u, 0u);
-        if (give) {
-          if (sp > 0) {
-            if (PHOS_SHARE_BOTTOM && !kDeep) {  // entry 0, the rest moves down
-              g = my_stack[0];
-              for (int e = 1; e < sp; ++e) my_stack[(e - 1) * kTraceBlock] = my_stack[e * kTraceBlock];
-              --sp;
-            } else {
-              g = pop();
-            }
-          } else {
-            const unsigned near = pend & (0u - pend);
-            g = make_uint2(cur.x, (cur.y & 0xffu) | ((pend ^ near) << 8));
-            cur.y = (cur.y & 0xffu) | (near << 8);
-          }
-        }
+        if (give) g = pop();
         const int from = take ? (int)__fns(don, 0, __popc(idle & lt_mask) + 1) : (int)lane;
         const uint32_t gx = __shfl_sync(0xffffffffu, g.x, from), gy = __shfl_sync(0xffffffffu, g.y, from);
         const float ox = __shfl_sync(0xffffffffu, r.ox, from), oy = __shfl_sync(0xffffffffu, r.oy, from), oz = __shfl_sync(0xffffffffu, r.oz, from);
@@ -526,16 +517,18 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
           r.flags = ff | kHelper;
           rd = make_raydir(wx, wy, wz);
           ridx = oo;
-          cur = make_uint2(gx, gy);
+          uint2 grp = make_uint2(gx, gy);
           sp = 0;
+          node = take_child(grp, rd.oct);
+          if (grp.y >> 8) push(grp);
           lt = 0u;
           has_ray = true;
         }
         changed = true;
       }
       if (changed) {  // vote again
-        tri_work = has_ray && lt != 0u;
-        node_work = has_ray && !tri_work && ((cur.y >> 8) != 0u || sp != 0);
+        tri_work = lt != 0u;
+        node_work = !tri_work && node != kNoNode;
         tl = __ballot_sync(0xffffffffu, tri_work);
         nl = __ballot_sync(0xffffffffu, node_work);
       }
