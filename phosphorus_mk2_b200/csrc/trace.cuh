@@ -35,7 +35,8 @@
 // iteration before the loads: -1..2.5 % (with a second prefetch 64 bytes on: -35 % on the terrain); L1::evict_last on node
 // loads, L1::no_allocate / evict_first on triangle loads: -0..19 %; not staging the next chunk ahead near the end of the
 // stream (claim at half of the current chunk / on demand): loses what the eager commit gained; vote bias 2 / 4, refill at
-// 4 / 8 idle lanes, sharing from 8 / 16 idle lanes: within the noise of the defaults.
+// 4 / 8 / 10 idle lanes, sharing from 8 / 16 idle lanes: within the noise of the defaults; 16- / 24-ray chunks: -1..4 %
+// (profiles/r02_sweep_eager_chunks.log).
 #pragma once
 #include "trace_ray.cuh"
 
