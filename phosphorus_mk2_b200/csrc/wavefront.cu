@@ -284,8 +284,15 @@ __global__ void __launch_bounds__(256) bin_window_kernel(const FrameArgs A, int 
 
 // integrator_t::operator() (spt.hpp:161-210) with li (:212-255), sample_bsdf (:257-305) and
 // terminate_path (:307-328); survivors are appended to the next ray stream.
+#ifndef PHOS_INT_HOIST_LIT
+#define PHOS_INT_HOIST_LIT 1
+#endif
 #ifndef PHOS_INTEGRATE_MIN_BLOCKS
-#define PHOS_INTEGRATE_MIN_BLOCKS 4  // 64 registers: measured best (profiles/r01_render_variants.log: 1 -> 4 blocks = +13 % on Cornell)
+// 3 blocks per SM = 80 registers.  With the loads of a slot batched into two round trips (above) the kernel holds ~25 loaded
+// values at once: at 64 registers (4 blocks, the r01 choice for the unbatched form) it spills 172 bytes and the batching
+// loses 1 %; at 80 it spills 68 bytes and gains 1.4 % on the Cornell box, 0.4 % on config 4; 48 registers: -10 %
+// (profiles/r02_render_integrate_batched_loads.log).
+#define PHOS_INTEGRATE_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kernel(const FrameArgs A, const phos_rays rays, const phos_rays sh,
                                  const uint32_t* __restrict__ slot_path, int cur, phos_rays next, uint32_t* __restrict__ next_path,
@@ -302,8 +309,19 @@ __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kern
   bool alive = false;
   uint32_t q = 0, nflags = 0;
   v3 no = V(0, 0, 0), nw = V(0, 0, 0), nbeta = V(0, 0, 0), rad = V(0, 0, 0);
-  if (valid && !(rays.flags[i] & PHOS_HIT)) {  // a miss adds beta * e_env (spt.hpp:199-202) and ends the path
-    const uint32_t p = slot_path[i];
+  // This kernel waits on memory (ncu: 58 % of the stall samples are long-scoreboard, 20 % of the issue slots used): what
+  // matters is the number of DEPENDENT round trips per slot.  Everything that hangs off the slot index alone is fetched in
+  // one of them — the hit flags, the path id, the material word and the verdict of the next-event shadow ray — and the
+  // fields of a hit slot in the next (the shadow direction and the light terms only where the shadow ray arrived).
+  uint32_t fl = 0, meshw = 0, sflags = PHOS_MASKED;
+  if (valid) {
+    fl = rays.flags[i];
+    q = slot_path[i];
+    meshw = rays.mesh[i];
+    sflags = sh.flags[i];
+  }
+  if (valid && !(fl & PHOS_HIT)) {  // a miss adds beta * e_env (spt.hpp:199-202) and ends the path
+    const uint32_t p = q;
     const size_t Q = A.Q;
     v3 rad = V(A.rad_in[i], A.rad_in[i + Q], A.rad_in[i + 2 * Q]);
     if (A.scene.environment >= 0) {
@@ -316,26 +334,38 @@ __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kern
     A.rad_final[p + Q] = rad.y;
     A.rad_final[p + 2 * Q] = rad.z;
   } else if (valid) {
-    q = slot_path[i];
     const size_t Q = A.Q;
+    const bool lit = !(sflags & (PHOS_HIT | PHOS_MASKED));  // the next-event shadow ray arrived
+    const DevMaterial* mt = A.scene.mats + (meshw >> 16);
+    // second round trip: all of these are independent loads
+    const uint32_t kind = __ldg(&mt->kind), nlobes = __ldg(&mt->nlobes);
     const uint32_t s = A.spp_begin + q / A.P, pix = A.pixel[q % A.P];
-    uint32_t depth = A.bounce;
     v3 beta = V(A.beta_in[i], A.beta_in[i + Q], A.beta_in[i + 2 * Q]);
     rad = V(A.rad_in[i], A.rad_in[i + Q], A.rad_in[i + 2 * Q]);
     const v3 o = V(rays.px[i], rays.py[i], rays.pz[i]), w = V(rays.wx[i], rays.wy[i], rays.wz[i]);
-    const v3 P = add(o, scl(w, rays.d[i]));
-    const v3 wo = neg(w);
+    const float dist = rays.d[i];
     const v3 n = V(A.n[i], A.n[i + Q], A.n[i + 2 * Q]);
-    const DevMaterial* mt = A.scene.mats + (rays.mesh[i] >> 16);
-    const bool emitter = __ldg(&mt->kind) == PHOS_MAT_EMITTER;
-    const uint32_t nlobes = __ldg(&mt->nlobes);
-    if (emitter && (depth == 0 || (rays.flags[i] & PHOS_SPECULAR)))
+    v3 swi = V(0, 0, 0), lw = V(0, 0, 0);
+    float lw_rcp_pdf = 0.0f;
+    if (PHOS_INT_HOIST_LIT && lit) {
+      swi = V(sh.wx[i], sh.wy[i], sh.wz[i]);
+      lw = V(A.lightw[i], A.lightw[i + Q], A.lightw[i + 2 * Q]);
+      lw_rcp_pdf = A.lightw[i + 3 * Q];
+    }
+    uint32_t depth = A.bounce;
+    const v3 P = add(o, scl(w, dist));
+    const v3 wo = neg(w);
+    const bool emitter = kind == PHOS_MAT_EMITTER;
+    if (emitter && (depth == 0 || (fl & PHOS_SPECULAR)))
       rad = add(rad, mul(beta, V(__ldg(&mt->e[0]), __ldg(&mt->e[1]), __ldg(&mt->e[2]))));
-    const uint32_t sflags = sh.flags[i];
-    if (!(sflags & (PHOS_HIT | PHOS_MASKED)) && nlobes != 0) {  // li(), spt.hpp:212-255; a 0-lobe BSDF evaluates to 0
-      const v3 swi = V(sh.wx[i], sh.wy[i], sh.wz[i]);
+    if (lit && nlobes != 0) {  // li(), spt.hpp:212-255; a 0-lobe BSDF evaluates to 0
+      if (!PHOS_INT_HOIST_LIT) {
+        swi = V(sh.wx[i], sh.wy[i], sh.wz[i]);
+        lw = V(A.lightw[i], A.lightw[i + Q], A.lightw[i + 2 * Q]);
+        lw_rcp_pdf = A.lightw[i + 3 * Q];
+      }
       const v3 f = bsdf_f(mt, n, swi, wo);
-      const v3 li = scl(mul(V(A.lightw[i], A.lightw[i + Q], A.lightw[i + 2 * Q]), f), A.lightw[i + 3 * Q]);  // (light.e * 4) * f * (1 / pdf)
+      const v3 li = scl(mul(lw, f), lw_rcp_pdf);  // (light.e * 4) * f * (1 / pdf)
       rad = add(rad, mul(beta, li));
     }
     ++depth;
