@@ -208,6 +208,16 @@ class RefScene:
             raise RuntimeError("cuda_t raised (see stderr)")
         return img, secs
 
+    def render_cuda_frames(self, spp: int, pps: int = 1, depth: int = 9, frames: int = 3):
+        """`frames` frames on ONE cuda_t made and preprocessed once, started / joined per frame (session.cpp:224-229: one
+        render per view on prepared devices).  Returns (last image, [seconds start..join per frame]); frame 0 is cold."""
+        cam = self._scene.camera
+        img = np.zeros((cam.film_height, cam.film_width, 4), np.float32)
+        secs = (C.c_double * frames)()
+        if self.lib.ref_render_frames_cuda(self.h, spp, pps, depth, frames, img.ctypes.data, secs) != 0:
+            raise RuntimeError("cuda_t raised (see stderr)")
+        return img, list(secs)
+
     def camera_rays(self, x0, y0, w, h, jx, jy, lens_u, lens_v):
         """The reference's own camera::perspective_kernel_t on one tile (w % 8 == 0, w * h <= 1024)."""
         n = w * h
@@ -271,6 +281,9 @@ class RefLib:
         L.ref_render_on.restype = C.c_double
         L.ref_render_aov.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_render_aov.restype = C.c_double
+        if hasattr(L, "ref_render_frames_cuda"):
+            L.ref_render_frames_cuda.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+            L.ref_render_frames_cuda.restype = C.c_int
         L.ref_bsdf_f.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
         L.ref_bsdf_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float] + [C.c_void_p] * 4
         L.ref_bsdf_sample.restype = C.c_int

@@ -329,6 +329,52 @@ double ref_render_aov(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int s
 }
 
 #ifdef REF_WITH_CUDA
+// Several frames on ONE cuda_t that is made and preprocessed once and then started / joined per frame — what
+// session_t does per view (plugins/blender/session.cpp:224-229: prepare_devices once, render per view).  A fresh tile
+// queue, sampler and (zeroed) film per frame; secs[i] = seconds around start..join of frame i, rgba holds the last
+// frame.  Frame 0 is the cold one (the device allocates its wavefront state and page-locked read-back slabs in it).
+// Returns 0, or -1 with a message on stderr if the device raised.
+int ref_render_frames_cuda(void* h, uint32_t spp, uint32_t pps, uint32_t depth, int frames, float* rgba, double* secs) {
+  auto* s = static_cast<ref_scene*>(h);
+  parsed_options_t options;
+  options.samples_per_pixel = spp;
+  options.paths_per_sample = pps;
+  options.path_depth = depth;
+  options.single_threaded = true;
+  options.host_only = true;
+  const uint32_t W = s->scene.camera.film.width, H = s->scene.camera.film.height;
+  render_buffer_t::descriptor_t format;
+  format.request(render_buffer_t::PRIMARY, 4);
+  xpu_t* device = nullptr;
+  int rc = 0;
+  try {
+    device = cuda_t::make(options, 0);
+    device->preprocess(s->scene);
+    for (int f = 0; f < frames; ++f) {
+      std::memset(rgba, 0, sizeof(float) * 4 * (size_t)W * H);
+      job::tiles_t* tiles = job::tiles_t::make(W, H, 32, format);
+      memory_film_t film;
+      film.rgba = rgba;
+      film.normals = nullptr;
+      film.width = W;
+      film.height = H;
+      sampler_t* sampler = new sampler_t(options);  // (leaked like everywhere in this file: its destructor is broken)
+      frame_state_t state(sampler, tiles, &film);
+      sampler->preprocess(s->scene);
+      const auto t0 = std::chrono::steady_clock::now();
+      device->start(s->scene, state);
+      device->join();
+      secs[f] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      delete tiles;
+    }
+  } catch (const std::exception& e) {
+    std::cerr << "ref_render_frames_cuda: " << e.what() << std::endl;
+    rc = -1;
+  }
+  delete device;
+  return rc;
+}
+
 int ref_cuda_device_count(void) { return cuda_t::device_count(); }
 
 // How many devices xpu_t::discover (src/xpu.cpp:7-9 + integration/xpu_discover.patch) returns, and how many are GPUs.

@@ -125,3 +125,14 @@ def test_normals_channel_and_thin_lens_through_the_reference_host_code(reflib_cu
     want = oracle.render(sc, acc.nodes_array(), acc.packets_array(), 8, 1, 3, seed=0, rcp_mode=2)
     err = float(np.abs(gimg[..., :3] - want[..., :3]).mean() / np.abs(want[..., :3]).mean())
     assert err < 1e-3
+
+
+def test_one_device_renders_several_frames(reflib_cuda):
+    """A device is prepared once and started per view (plugins/blender/session.cpp:224-229): the second and third
+    start / join of ONE cuda_t return the film of the first (same seed, fresh tile queue and film per frame)."""
+    sc = scenes.cornell_box(96, 64)
+    rs = reflib_cuda.scene(sc)
+    once, _ = rs.render_cuda(spp=8, pps=1, depth=4)
+    last, secs = rs.render_cuda_frames(spp=8, pps=1, depth=4, frames=3)
+    assert len(secs) == 3 and all(s > 0 for s in secs)
+    assert np.array_equal(once, last)
