@@ -85,6 +85,15 @@ namespace phos {
 #ifndef PHOS_SHARE_MIN_UNITS
 #define PHOS_SHARE_MIN_UNITS 2
 #endif
+// The end of the stream: once fewer than PHOS_LAZY_TAIL chunks per warp are unclaimed, a warp stages the chunk after the
+// current one only when half of the current one is taken — when the cursor runs dry it then holds part of ONE chunk, not
+// one and a half on average.  0 = always stage ahead.  (One claim site in the loop either way: a first version with a
+// third inlined `claim` grew the kernel from 2288 to 2960 instructions and lost 4 % on every stream.)  Measured on two
+// boxes (profiles/r02_sweep_lazy_staging.log): windows of 4-8 chunks give +0.5..2.5 % on the bounce stream, +0.5..1 % on
+// the shadow stream, -0.3..0.5 % on coherent rays — inside the box noise; off by default.
+#ifndef PHOS_LAZY_TAIL
+#define PHOS_LAZY_TAIL 0
+#endif
 constexpr uint32_t kNoNode = 0xffffffffu;     // "no node left to test" (Ray traversal state)
 constexpr int kChunk = PHOS_CHUNK;           // rays per claimed chunk
 constexpr int kRefillMin = PHOS_REFILL_MIN;  // idle lanes that trigger a refill
@@ -174,6 +183,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
   uint32_t cur_base = 0, nxt_base = 0;  // ray indices fit 32 bits: launch_trace splits longer streams
   uint32_t cur_cnt = 0, taken = 0, nxt_cnt = 0;
   bool nxt_tma = false, exhausted = false;
+  bool lazy = false;  // PHOS_LAZY_TAIL: the current chunk lies in the last part of the stream
 
   bool first_claim = true;
   auto claim = [&](int buf) {  // claim the next chunk of the stream and start staging it into `buf`
@@ -234,7 +244,13 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
     cur_cnt = nxt_cnt;
     taken = 0;
     __syncwarp();  // every lane is done reading the buffer we are about to refill
-    claim(b ^ 1);
+    if (PHOS_LAZY_TAIL) {
+      const unsigned long long window = (unsigned long long)gridDim.x * (kTraceWarps * kChunk * PHOS_LAZY_TAIL);
+      lazy = (unsigned long long)cur_base + window >= N;
+      nxt_cnt = 0;  // claimed from the refill loop below
+    } else {
+      claim(b ^ 1);
+    }
     return true;
   };
   claim(1);
@@ -407,6 +423,7 @@ __global__ void __launch_bounds__(kTraceBlock, PHOS_MIN_BLOCKS) trace_kernel(con
             }
           }
           taken += take;
+          if (PHOS_LAZY_TAIL && nxt_cnt == 0 && !exhausted && (!lazy || 2u * taken >= cur_cnt)) claim(cur_buf ^ 1);
           idle = __ballot_sync(0xffffffffu, !has_ray);
         }
         continue;  // new rays: vote again
