@@ -11,10 +11,15 @@
 
 namespace phos {
 
-constexpr int kPipe = 4;                     // host-pointer trace: chunks in flight
-constexpr uint64_t kPipeChunk = 1ull << 18;  // rays per chunk (8 MiB in): measured best on the B200 box — smaller
-                                             // chunks are bound by the ~20 us the host pays per copy call, larger
-                                             // ones overlap less of the up-link, the SMs and the down-link
+#ifndef PHOS_PIPE
+#define PHOS_PIPE 4
+#endif
+constexpr int kPipe = PHOS_PIPE;             // host-pointer trace: chunks in flight (<= 8: their cursors are d_counters[16..24))
+constexpr uint64_t kPipeChunk = 1ull << 17;  // rays per chunk (512 KiB per array row, 4 MiB in): measured best on three B200
+                                             // boxes with 4 chunks in flight and two up-copy streams — 1200-1230 Mrays/s per
+                                             // 2 M-ray frame against 1130-1160 at 2^18 and 1110-1140 at 112-120 Ki (rows that
+                                             // do not start on a 64 KiB boundary of the page-locked slab); 3 / 6 / 8 chunks in
+                                             // flight: -1..5 % (profiles/r02_e2e_chunks.log)
 
 // One staging slot of the host-pointer trace pipeline.  Copies in, traversal and copies out run on three
 // DEDICATED streams (phos_ctx::s_in / s_cmp / s_out) chained by these events: with one stream per slot the
