@@ -422,6 +422,8 @@ int phos_cuda_trace(phos_ctx* ctx, const phos_rays* rays, uint64_t n) {
   if (const char* e = std::getenv("PHOS_E2E_WB_CTAS")) wb_ctas = std::max(1, std::atoi(e));
   const char* dbg = std::getenv("PHOS_E2E_DEBUG");  // timing probes only (tools/e2e_probe.py): "noin" / "noout" skip a stage
   const bool dbg_noin = dbg && strstr(dbg, "noin"), dbg_noout = dbg && strstr(dbg, "noout");
+  // (Chunk sizes tapering towards both ends of the stream — chunk / 4, chunk / 2, chunk ... chunk / 2, chunk / 4 — measured
+  // twice, r01 and profiles/r02_e2e_chunks.log: -1 % at 128 Ki, +1 % at 256 Ki.  Not kept.)
   for (uint64_t base = 0; ok && base < n; base += chunk, slot = (slot + 1) % kPipe) {
     const uint64_t cnt = std::min(chunk, n - base);
     PipeLane& L = ctx->pipe[slot];

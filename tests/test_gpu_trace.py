@@ -108,6 +108,33 @@ def test_pinned_stream_sparse_write_back(device, oracle, monkeypatch):
         assert np.array_equal(a[closest], b[closest]), f
 
 
+def test_long_pinned_stream_equals_the_device_resident_query(device, monkeypatch):
+    """A long page-locked stream through the host-pointer pipeline (several chunks in flight, slots reused, a ragged last
+    chunk): every ray exactly once, same bits as the device-resident query."""
+    sc = scenes.heightfield(96)
+    device.preprocess(sc)
+    monkeypatch.setenv("PHOS_PIPE_CHUNK", "32768")
+    n = 9 * 32768 + 12345
+    src = raysets.aimed_rays(sc, n, seed=91)
+    sh = raysets.as_shadow(src, seed=92, masked_fraction=0.1)
+    for f in ("d", "flags"):
+        getattr(src, f)[1::4] = getattr(sh, f)[1::4]
+    dr = device.device_rays(n)
+    dr.upload(src)
+    device.trace_device(dr)
+    want = dr.download()
+    dr.free()
+    closest = (src.flags & 4) == 0
+    pr = pinned_ray_batch(n)
+    for f in ("px", "py", "pz", "wx", "wy", "wz", "d", "u", "v", "mesh", "face", "flags"):
+        getattr(pr, f)[:] = getattr(src, f)
+    device.trace(pr)
+    assert np.array_equal(pr.flags, want.flags)
+    for f in ("d", "u", "v", "mesh", "face"):
+        assert np.array_equal(bits(getattr(pr, f))[closest], bits(getattr(want, f))[closest]), f
+    pr.free()
+
+
 def test_empty_stream_and_call_order_errors(device):
     fresh = CudaDevice.make(Options(), 0)
     with pytest.raises(PhosError):
