@@ -36,7 +36,8 @@
 // loads, L1::no_allocate / evict_first on triangle loads: -0..19 %; not staging the next chunk ahead near the end of the
 // stream (claim at half of the current chunk / on demand): loses what the eager commit gained; vote bias 2 / 4, refill at
 // 4 / 8 / 10 idle lanes, sharing from 8 / 16 idle lanes: within the noise of the defaults; 16- / 24-ray chunks: -1..4 %
-// (profiles/r02_sweep_eager_chunks.log).
+// (profiles/r02_sweep_eager_chunks.log); hit acceptance as predicated moves instead of a branch: -0.5..1.5 % (the branch is
+// warp-uniformly not taken on most triangle tests; profiles/r02_sweep_branchfree_accept.log).
 #pragma once
 #include "trace_ray.cuh"
 
