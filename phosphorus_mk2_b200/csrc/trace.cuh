@@ -37,7 +37,11 @@
 // stream (claim at half of the current chunk / on demand): loses what the eager commit gained; vote bias 2 / 4, refill at
 // 4 / 8 / 10 idle lanes, sharing from 8 / 16 idle lanes: within the noise of the defaults; 16- / 24-ray chunks: -1..4 %
 // (profiles/r02_sweep_eager_chunks.log); hit acceptance as predicated moves instead of a branch: -0.5..1.5 % (the branch is
-// warp-uniformly not taken on most triangle tests; profiles/r02_sweep_branchfree_accept.log).
+// warp-uniformly not taken on most triangle tests; profiles/r02_sweep_branchfree_accept.log); deferred leaves — a lane
+// with pending leaf triangles keeps taking part in node steps, the leaves those hit wait as a second set in shared
+// memory: the warp-level simulator (tools/warp_sim, which reproduces this kernel's step counters) predicts 5-7 % fewer
+// issue slots per ray, the build does the predicted visits and is 0.5-7 % SLOWER (+112 SASS instructions, a spill slot;
+// profiles/r02_warp_sim_deferred_leaves.log).
 #pragma once
 #include "trace_ray.cuh"
 
