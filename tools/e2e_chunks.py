@@ -29,3 +29,5 @@ chunks = sys.argv[1].split(",") if len(sys.argv) > 1 else ("65536", "98304", "13
 for rep in range(2):
     for ch in chunks:
         run(f"chunk {ch}", PHOS_PIPE_CHUNK=ch)
+    for c in (sys.argv[2].split(",") if len(sys.argv) > 2 else ()):
+        run(f"chunk {chunks[0]}, {c} write-back CTAs", PHOS_PIPE_CHUNK=chunks[0], PHOS_E2E_WB_CTAS=c)
