@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(256) bin_window_kernel(const FrameArgs A, int 
 // 3 blocks per SM = 80 registers.  With the loads of a slot batched into two round trips (above) the kernel holds ~25 loaded
 // values at once: at 64 registers (4 blocks, the r01 choice for the unbatched form) it spills 172 bytes and the batching
 // loses 1 %; at 80 it spills 68 bytes and gains 1.4 % on the Cornell box, 0.4 % on config 4; 48 registers: -10 %
-// (profiles/r02_render_integrate_batched_loads.log).
+// (profiles/r02_render_integrate_batched_loads.log); at 2 blocks (102 registers, no spill at all) it loses 4.3 % / 1.4 %: the
+// spill-free kernel is not the fast one.
 #define PHOS_INTEGRATE_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(256, PHOS_INTEGRATE_MIN_BLOCKS) integrate_kernel(const FrameArgs A, const phos_rays rays, const phos_rays sh,
