@@ -139,3 +139,44 @@ def test_repack_splits_oversized_leaves(emul, oracle):
     got, _, _, stats = run_emul(emul, nodes, packets, rays)
     assert stats[3] <= 15
     assert len(mismatches(rays, got, want)) == 0
+
+
+def test_warp_level_schedule_of_the_kernel_gives_the_one_ray_results(oracle):
+    """tools/warp_sim runs trace_kernel's scheduling on the host — 32 lanes, refill at >= 6 idle lanes, one node step or one
+    triangle step per iteration by the weighted vote, the next node committed at the end of a node step — over the device's
+    own node_test / mt_triangle / accept_hit.  Closest hits and shadow verdicts must be those of the oracle for every ray,
+    with the shipped policy and with leaves deferred behind node steps (a different ORDER of the same tests)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    here = os.path.join(root, "tools", "warp_sim")
+    so = os.path.join(here, "libsim_test.so")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I/usr/local/cuda/include",
+                    os.path.join(here, "sim.cpp"), os.path.join(root, "phosphorus_mk2_b200", "csrc", "repack.cpp"), "-o", so], check=True)
+    L = C.CDLL(so)
+
+    class Params(C.Structure):
+        _fields_ = [("refill_min", C.c_int), ("tri_bias", C.c_int), ("defer", C.c_int), ("defer_shadow_only", C.c_int),
+                    ("tri_min_lanes", C.c_int), ("hint", C.c_int)]
+
+    sc = scenes.heightfield(120, seed=4)
+    a = Accel(sc)
+    nodes, packets = a.nodes_array(), a.packets_array()
+    rays = raysets.aimed_rays(sc, 6000, seed=12)
+    sh = raysets.as_shadow(raysets.aimed_rays(sc, 6000, seed=13), seed=14, masked_fraction=0.1)
+    for f in ("px", "py", "pz", "wx", "wy", "wz", "d", "flags"):
+        getattr(rays, f)[1::3] = getattr(sh, f)[1::3]
+    want, _ = oracle.traverse(nodes, packets, rays)
+    closest = (rays.flags & 6) == 0
+    for kw in (dict(refill_min=6, tri_bias=3, defer=0), dict(refill_min=6, tri_bias=2, defer=2)):
+        s = rays.as_struct()
+        out = (C.c_uint64 * 10)()
+        d = np.zeros(rays.n, np.float32)
+        fl = np.zeros(rays.n, np.uint32)
+        p = Params(**kw)
+        assert L.warp_sim(C.c_void_p(nodes.ctypes.data), C.c_uint32(len(nodes) // 288), C.c_void_p(packets.ctypes.data),
+                          C.c_uint32(len(packets) // 384), C.byref(s), C.c_uint64(rays.n), C.c_int(7), C.byref(p), out,
+                          C.c_void_p(d.ctypes.data), C.c_void_p(fl.ctypes.data)) == 0
+        assert np.array_equal(fl, want.flags), kw
+        assert np.array_equal(d[closest].view(np.uint32), want.d[closest].view(np.uint32)), kw
+        assert out[8] == int(((rays.flags & 2) == 0).sum())  # every unmasked ray traced exactly once
