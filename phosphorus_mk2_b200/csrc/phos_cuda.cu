@@ -228,6 +228,14 @@ phos_ctx* phos_cuda_create(int device, const phos_options* options) {
        cuda_ok(nullptr, cudaEventCreate(&ctx->ev_end), "cudaEventCreate") &&
        cuda_ok(nullptr, cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long)), "cudaMalloc(counters)") &&
        cuda_ok(nullptr, cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long)), "cudaMemset(counters)");
+  // tuning probe: shared-memory carve-out of the traversal kernel in % of the maximum (the rest of the 256 KB is L1); the
+  // default leaves the choice to the driver (the smallest carve-out that fits the resident CTAs)
+  if (const char* e = std::getenv("PHOS_TRACE_CARVEOUT")) {
+    const int pct = std::atoi(e);
+    cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(trace_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaGetLastError();
+  }
   int blocks = 0;
   ok = ok && cuda_ok(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, trace_kernel<false, false>, kTraceBlock, 0),
                      "occupancy(trace_kernel)");
